@@ -1,0 +1,189 @@
+/* ptcore.h — C ABI of the B200-native path-tracing core (libptcore.so).
+ *
+ * This is the drop-in boundary for the reference's device layer.  Each entry point replaces one
+ * piece of `class DevicePathTracer` (reference src/DevicePathTracer.h:167-392); the C++ shim
+ * multi-gpu-path-tracer_b200/csrc/host/DevicePathTracer.h keeps the reference's class signature
+ * and forwards here.  Plain pointers and sizes only: no STL, no torch, no exceptions cross it.
+ *
+ * Conventions
+ *   - every function returns 0 on success, otherwise a cudaError_t value or a PT_ERR_* code;
+ *     ptcore_last_error(h) returns a static/handle-owned message for the last failure.
+ *     (The reference has no return codes: checkCudaErrors prints and exit(99)s,
+ *     src/cuda_utils.h:6-16.  The C++ shim reproduces that on a non-zero return.)
+ *   - `stream` parameters are `cudaStream_t` passed as void* (NULL = legacy default stream).
+ *   - a handle is bound to one device; calls may come from any host thread, and
+ *     ptcore_render_* may be called concurrently on different streams (as StreamThread does,
+ *     reference src/StreamThread.h:83-84); setters must not race with renders (same contract as
+ *     the reference: setters run while the workers are parked, src/RenderManager.h:146-183).
+ *   - image space is the reference's: RenderTask offsets are in bottom-up pixel space and the
+ *     framebuffer row 0 is the TOP image row (src/DevicePathTracer.h:77-79).
+ */
+#ifndef PTCORE_H
+#define PTCORE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTCORE_ABI_VERSION 1
+
+typedef struct ptcore ptcore_t;
+
+/* error codes outside the cudaError_t range */
+enum {
+    PT_OK = 0,
+    PT_ERR_INVALID_ARGUMENT = 100001,
+    PT_ERR_NO_SCENE = 100002,
+    PT_ERR_NO_FRAMEBUFFER = 100003,
+    PT_ERR_UNSUPPORTED = 100004,
+    PT_ERR_SYSTEM = 100005
+};
+
+/* Same enumerators and order as `enum material_type`, reference src/HostScene.h:20-26. */
+enum {
+    PT_MAT_LAMBERTIAN = 0,   /* reference src/material.h:110-127 (dead code there, live here) */
+    PT_MAT_METAL = 1,        /* src/material.h:130-144 */
+    PT_MAT_DIELECTRIC = 2,   /* src/material.h:146-179 */
+    PT_MAT_DIFFUSE_LIGHT = 3,/* src/material.h:210-217 */
+    PT_MAT_UNIVERSAL = 4     /* src/material.h:40-102 — the only class the reference instantiates */
+};
+
+/* 44 bytes; identical to the material record of the .ptscene file. */
+typedef struct PtMaterial {
+    int32_t type;      /* PT_MAT_* */
+    float base[3];     /* baseColorFactor / albedo */
+    float emis[3];     /* emissiveFactor (UNIVERSAL: multiplied by 50, src/material.h:80-86) / light colour */
+    int32_t base_tex;  /* texture index or -1 */
+    int32_t emis_tex;  /* texture index or -1 */
+    float fuzz;        /* METAL */
+    float ior;         /* DIELECTRIC */
+} PtMaterial;
+
+/* float3 texels in 0..255, row 0 = top row of the image file: HostTexture, src/HostScene.h:48-52 */
+typedef struct PtTexture {
+    int32_t width, height;
+    const float *rgb; /* width*height*3 */
+} PtTexture;
+
+/* Flat view of HostScene (src/HostScene.h:54-58). All pointers are HOST pointers and are only
+ * read during ptcore_upload_scene. */
+typedef struct PtSceneDesc {
+    int32_t n_tris;
+    const float *tri_pos;   /* [n_tris][3 vertices][xyz] */
+    const float *tri_uv;    /* [n_tris][3 vertices][uv]  */
+    const int32_t *tri_mat; /* [n_tris] material index   */
+    int32_t n_spheres;
+    const float *sph;       /* [n_spheres][cx,cy,cz,r]   */
+    const int32_t *sph_mat; /* [n_spheres]               */
+    int32_t n_mats;
+    const PtMaterial *mats;
+    int32_t n_tex;
+    const PtTexture *tex;
+} PtSceneDesc;
+
+/* CameraConfig, reference src/CameraConfig.h:5-17 (pitch/yaw are UI state and not part of the path). */
+typedef struct PtCamera {
+    float look_from[3];
+    float front[3];
+    float vfov; /* degrees */
+    float hfov; /* degrees, independent of the aspect ratio (src/camera.h:24-35) */
+} PtCamera;
+
+/* RenderTask, reference src/DevicePathTracer.h:19-25 (without the host-side `time`). */
+typedef struct PtTile {
+    int32_t width, height, offset_x, offset_y;
+} PtTile;
+
+enum { /* ptcore_set_option keys */
+    PT_OPT_KERNEL = 1,       /* PT_KERNEL_* */
+    PT_OPT_COUNT_TESTS = 2,  /* 1: count box/triangle tests per ray (stats build of the kernel, slower) */
+    PT_OPT_BVH_LEAF_MAX = 3, /* max triangles per leaf for the next upload (default 4) */
+    PT_OPT_BLOCKS_PER_SM = 4,/* persistent grid = SMs x this (0 = auto) */
+    PT_OPT_SLICE_SPP = 5,    /* samples a lane runs on one pixel before handing it back to the pool (0 = whole pixel) */
+    PT_OPT_BVH_REFERENCE_LIKE = 6 /* 1: build the tree with the reference's own heuristic (attribution runs only) */
+};
+enum {
+    PT_KERNEL_PERSISTENT = 0, /* persistent-thread wavefront (default) */
+    PT_KERNEL_DIRECT = 1      /* one thread per pixel, no refill: the plain parity slice */
+};
+
+typedef struct PtStats {
+    uint64_t samples;     /* camera paths started */
+    uint64_t rays;        /* closest-hit queries (camera + bounce segments) */
+    uint64_t box_tests;   /* only with PT_OPT_COUNT_TESTS */
+    uint64_t tri_tests;   /* only with PT_OPT_COUNT_TESTS (BVH leaf tests; light-pdf tests excluded) */
+    uint64_t light_tests; /* only with PT_OPT_COUNT_TESTS */
+    uint64_t launches;    /* kernel launches issued by this handle */
+    uint32_t bvh_nodes, bvh_leaves, bvh_depth, n_lights;
+    double bvh_build_ms;  /* host time of the last scene compile */
+    double sah_cost;
+    uint64_t scene_bytes; /* size of the compiled device blob */
+} PtStats;
+
+/* ---- lifetime (DevicePathTracer ctor/dtor, src/DevicePathTracer.h:169-192,372-377) ---- */
+int ptcore_abi_version(void);
+int ptcore_create(int device, ptcore_t **out);
+int ptcore_destroy(ptcore_t *h);
+const char *ptcore_last_error(const ptcore_t *h); /* h may be NULL: last error of ptcore_create */
+
+/* ---- scene (reloadWorld + loadTextures/loadMaterials/loadTrianglesWithTextures, :241-340;
+ *      replaces create_world<<<1,1>>> / create_lights<<<1,1>>> and the device-side BVH build of
+ *      src/bvh.h:20-176 with a host SAH build + one bulk upload) ---- */
+int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *scene);
+/* re-copies the already compiled scene blob host->device on `stream` (end-to-end timing, hot reload) */
+int ptcore_reupload_scene(ptcore_t *h, void *stream, uint64_t *bytes_copied);
+
+/* ---- camera (reloadCamera :230-239 + the by-value CameraConfig of every launch :210) ---- */
+int ptcore_set_camera(ptcore_t *h, const PtCamera *cam);
+
+/* ---- parameters (setSamplesPerPixel / setRecursionDepth / setThreadBlockSize :360-370) ---- */
+int ptcore_set_params(ptcore_t *h, uint32_t samples_per_pixel, uint32_t recursion_depth);
+int ptcore_set_thread_block_size(ptcore_t *h, uint32_t bx, uint32_t by); /* accepted for API parity; the persistent kernel ignores it */
+int ptcore_set_option(ptcore_t *h, int key, int64_t value);
+
+/* ---- framebuffer (setFramebuffer :342-358; replaces render_init<<<>>> and the 48 B/pixel
+ *      curandState array: XORWOW states are derived from the pixel index on the fly) ----
+ * rgb: W*H*3 bytes, yuv: W*H*3/2 bytes (I420), DEVICE or MANAGED pointers; yuv may be NULL. */
+int ptcore_bind_framebuffer(ptcore_t *h, uint8_t *rgb, uint8_t *yuv, uint32_t width, uint32_t height);
+
+/* ---- render (renderTaskAsync :194-214 / synchronizeStream :222-226 / waitForRenderTask :216-220) ---- */
+int ptcore_render_tile_async(ptcore_t *h, int32_t offset_x, int32_t offset_y, int32_t width, int32_t height, void *stream);
+int ptcore_render_tiles_async(ptcore_t *h, const PtTile *tiles, int32_t n_tiles, void *stream);
+int ptcore_sync(ptcore_t *h, void *stream);
+int ptcore_wait(ptcore_t *h);
+
+/* Whole-frame convenience with HOST output buffers: binds an internal device framebuffer, renders
+ * every pixel, copies RGB (and I420 if yuv_host != NULL) back.  What `e2e` in bench.py times. */
+int ptcore_render_frame_host(ptcore_t *h, uint32_t width, uint32_t height, uint8_t *rgb_host, uint8_t *yuv_host);
+
+/* ---- statistics ---- */
+int ptcore_get_stats(ptcore_t *h, PtStats *out); /* synchronises the device */
+int ptcore_reset_stats(ptcore_t *h);
+
+/* ---- multi-GPU plumbing: a tile counter shared by the ranks of one node (POSIX shared memory).
+ *      Replaces the per-frame static rectangles of RenderManager/TaskGenerator
+ *      (src/RenderManager.h:42-59, src/Scheduling/TaskGenerator.h:58-80) with dynamic claims. ---- */
+typedef struct pt_tileq pt_tileq_t;
+int pt_tileq_open(const char *name, int create, pt_tileq_t **out);
+int64_t pt_tileq_claim(pt_tileq_t *q, int64_t count, int64_t limit); /* returns first claimed index, or -1 when >= limit */
+int pt_tileq_reset(pt_tileq_t *q);
+int pt_tileq_close(pt_tileq_t *q, int unlink_name);
+
+/* ---- scene files (SceneLoader::load, src/HostScene.cpp:98-139, without assimp) ----
+ * Loads .glb/.gltf/.obj/.ptscene into library-owned memory exposed as a PtSceneDesc. */
+typedef struct ptscene ptscene_t;
+int ptscene_load(const char *path, ptscene_t **out, char *err, size_t err_len);
+const PtSceneDesc *ptscene_desc(const ptscene_t *s);
+int ptscene_save(const ptscene_t *s, const char *path);
+void ptscene_free(ptscene_t *s);
+
+/* P6 writer for an RGB8 framebuffer (the README's out.ppm, README.md:52-58; the reference has no writer) */
+int pt_write_ppm(const char *path, const uint8_t *rgb, uint32_t width, uint32_t height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTCORE_H */
