@@ -1,0 +1,381 @@
+#!/usr/bin/env python3
+"""bench.py — Msamples/s (and Mrays/s) of the path-tracing hot path on BASELINE config 2:
+models/cornell_duck.glb, 1920x1080, 1024 spp, max depth 10, the reference's default camera.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA core (N > 1: under torchrun)
+    python bench.py --impl reference [...]                         the reference's own CPU implementation
+
+A "step" is one whole frame (W*H*spp camera paths).  `value` is whole-job throughput with the compiled
+scene resident in HBM; `e2e` is the same frame through the C ABI with HOST buffers (scene blob H2D from
+pinned memory + camera + render + RGB/I420 D2H inside the timed region).  N > 1 splits the SAME frame
+over the ranks (strong scaling): dynamic tile claims from a node-wide counter, one NCCL reduce at frame end.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WIDTH, HEIGHT, SPP, DEPTH = 1920, 1080, 1024, 10
+WORKLOAD = f"cornell_duck {WIDTH}x{HEIGHT} spp={SPP} depth={DEPTH} (BASELINE configs[1])"
+SCENE = ROOT / "tests" / "golden" / "cornell_duck.ptscene.gz"
+# algorithmic work per ray on OUR tree, from the core's own counters
+FLOPS_PER_RAY = lambda n_box, n_tri: 24.0 * n_box + 45.0 * n_tri + 180.0
+BYTES_PER_RAY = lambda n_box, n_tri: 32.0 * n_box + 48.0 * n_tri + 168.0
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ["clocks.sm", "clocks.max.sm", "power.draw", "clocks_event_reasons.hw_slowdown", "clocks_event_reasons.hw_thermal_slowdown",
+              "clocks_event_reasons.sw_thermal_slowdown", "clocks_event_reasons.sw_power_cap"]
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + ",".join(self.FIELDS), "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v == "Active":
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def flat_scene_file(tmpdir: Path) -> Path:
+    import ptb200
+    flat = tmpdir / "cornell_duck.ptscene"
+    if not flat.exists():
+        flat.write_bytes(ptb200.load_scene_file(SCENE).to_ptscene_bytes())
+    return flat
+
+
+def cpu_reference_sample(threads: int, rect=(640, 360, 640, 360), spp=4):
+    """Times the reference's CPU implementation (oracle/_ref/ref_cpu: its own headers host-compiled, OpenMP) on a
+    bounded sample of the workload: the centre `rect` of the 1920x1080 frame at `spp` samples, depth 10.
+    Falls back to the plain-C port (oracle/_build) when the reference-derived binary is not there."""
+    import tempfile
+    ref_cpu = ROOT / "oracle" / "_ref" / "ref_cpu"
+    sample = f"{WIDTH}x{HEIGHT} frame, centre rect {rect[2]}x{rect[3]} at ({rect[0]},{rect[1]}), spp={spp}, depth={DEPTH}"
+    n_samples = rect[2] * rect[3] * spp
+    if ref_cpu.exists():
+        with tempfile.TemporaryDirectory() as td:
+            flat = flat_scene_file(Path(td))
+            out = subprocess.run([str(ref_cpu), str(flat), str(WIDTH), str(HEIGHT), str(spp), str(DEPTH), "-", "--rect", *map(str, rect), "--threads", str(threads)],
+                                 check=True, capture_output=True, text=True).stdout
+        j = json.loads(out.strip().splitlines()[-1])
+        return dict(value=j["msamples_per_s"], unit="Msamples/s", cores=threads, kind="reference", sample=sample, seconds=j["seconds"], samples=n_samples)
+    sys.path.insert(0, str(ROOT / "tests"))
+    import _oracle
+    import ptb200
+    orc = _oracle.load()
+    scene = ptb200.load_scene_file(SCENE)
+    t0 = time.perf_counter()
+    orc.render(scene, WIDTH, HEIGHT, spp, DEPTH, rect=rect, threads=threads)
+    sec = time.perf_counter() - t0
+    return dict(value=n_samples / sec / 1e6, unit="Msamples/s", cores=threads, kind="port", sample=sample, seconds=sec, samples=n_samples)
+
+
+def gpu_reference_sample(spp=16):
+    """The reference's own CUDA renderer (oracle/_ref/ref_gpu: RenderManager + DevicePathTracer + kernels, unmodified,
+    compiled for sm_100) on the same box: full 1920x1080 frame at reduced spp, frame >= 2 timed."""
+    import tempfile
+    ref_gpu = ROOT / "oracle" / "_ref" / "ref_gpu"
+    if not ref_gpu.exists():
+        return {"unavailable": "oracle/_ref/ref_gpu not built (needs /root/reference at build time)"}
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            flat = flat_scene_file(Path(td))
+            r = subprocess.run([str(ref_gpu), str(flat), str(WIDTH), str(HEIGHT), str(spp), str(DEPTH), "-", "--frames", "3"], capture_output=True, text=True, timeout=900)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("REF_GPU_JSON ")]
+        if r.returncode != 0 or not line:
+            return {"unavailable": f"ref_gpu exited {r.returncode}: {(r.stderr or r.stdout)[-200:]}"}
+        j = json.loads(line[-1][len("REF_GPU_JSON "):])
+        return dict(value=j["msamples_per_s"], unit="Msamples/s", kind="reference CUDA renderer (unmodified kernels, sm_100, 8x8 blocks)",
+                    sample=f"{WIDTH}x{HEIGHT} spp={spp} depth={DEPTH}, mean of frames 2-3", seconds=j["seconds"], init_seconds=j["init_seconds"])
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    threads = host_cores()
+    for _ in range(args.warmup):
+        cpu_reference_sample(threads, rect=(880, 500, 160, 80), spp=1)
+    vals, secs = [], []
+    last = None
+    for _ in range(args.steps):
+        last = cpu_reference_sample(threads)
+        vals.append(last["value"]); secs.append(last["seconds"])
+    value = sum(last["samples"] for _ in vals) / sum(secs) / 1e6
+    line = {"impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "reference model cornell_duck (converted fixture), fixed XORWOW seeds",
+            "config": {"workload": WORKLOAD, "sample_per_step": last["sample"]},
+            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spp", type=int, default=SPP, help="override for quick experiments (a non-default value is flagged in config)")
+    ap.add_argument("--kernel", default="persistent", choices=["persistent", "direct"])
+    ap.add_argument("--tile", default="64x32")
+    ap.add_argument("--claim", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import ptb200
+    sched = ptb200.sched
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    spp = args.spp
+    scene = ptb200.load_scene_file(SCENE)
+    pt = ptb200.PathTracer(local_rank)
+    pt.upload_scene(scene)
+    pt.set_camera()
+    pt.set_params(spp, DEPTH)
+    pt.set_option(ptb200.PT_OPT_KERNEL, ptb200.PT_KERNEL_DIRECT if args.kernel == "direct" else ptb200.PT_KERNEL_PERSISTENT)
+
+    tw, th = (int(x) for x in args.tile.split("x"))
+    if world == 1:
+        tiles = [(0, 0, WIDTH, HEIGHT)]
+        claim = 1
+    else:
+        tiles = sched.interleave(sched.make_tiles(WIDTH, HEIGHT, tw, th), world * 4)
+        claim = args.claim or max(1, len(tiles) // (world * 8))
+    plan = sched.FramePlan(WIDTH, HEIGHT, tiles, claim)
+    rr = sched.RankRenderer(pt, WIDTH, HEIGHT, device)
+
+    queue = None
+    if world > 1:
+        qname = f"/ptb200_tileq_{os.environ.get('MASTER_PORT', '0')}"
+        if rank == 0:
+            queue = ptb200.TileQueue(qname, create=True)
+        dist.barrier()
+        if rank != 0:
+            queue = ptb200.TileQueue(qname, create=False)
+        dist.barrier()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def step():
+        """one frame; returns device milliseconds (CUDA events on the launching stream)"""
+        flush.zero_()
+        if world > 1:
+            barrier()
+            if rank == 0:
+                queue.reset()
+            barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rr.render_frame(plan, queue, rank, world)
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    # ---- algorithmic work per ray on our tree (stats build of the kernel, low spp, outside the timed region) ----
+    per_ray = None
+    if rank == 0:
+        pt.set_option(ptb200.PT_OPT_COUNT_TESTS, 1)
+        pt.set_params(4, DEPTH)
+        pt.reset_stats()
+        pt.render_tiles_async([(0, 0, WIDTH, HEIGHT)])
+        st = pt.stats()
+        per_ray = dict(box=st["box_tests"] / st["rays"], tri=st["tri_tests"] / st["rays"], light=st["light_tests"] / st["rays"], rays_per_sample=st["rays"] / st["samples"])
+        pt.set_option(ptb200.PT_OPT_COUNT_TESTS, 0)
+        pt.set_params(spp, DEPTH)
+    pt.reset_stats()
+
+    for _ in range(args.warmup):
+        step()
+    pt.reset_stats()
+    rr.launches = 0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    ms = [step() for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = float(sum(ms))
+    st = pt.stats()
+    if world > 1:
+        t = torch.tensor([total_ms, float(st["rays"]), float(st["launches"])], dtype=torch.float64, device=device)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_ms, rays, launches = float(tmax[0]), float(t[1]), int(t[2])
+    else:
+        rays, launches = float(st["rays"]), int(st["launches"])
+    samples_per_step = WIDTH * HEIGHT * spp
+    value = samples_per_step * args.steps / (total_ms / 1e3) / 1e6
+    mrays = rays / (total_ms / 1e3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        rgb_host = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.uint8).pin_memory()
+        yuv_host = torch.empty((WIDTH * HEIGHT * 3 // 2,), dtype=torch.uint8).pin_memory()
+        rgb_np, yuv_np = rgb_host.numpy(), yuv_host.numpy()
+        h2d = d2h = 0
+
+        def e2e_step():
+            nonlocal h2d, d2h
+            if world > 1:
+                barrier()
+                if rank == 0:
+                    queue.reset()
+                barrier()
+            t0 = time.perf_counter()
+            h2d = pt.reupload_scene() + 32  # compiled scene blob from pinned host memory + the camera struct
+            pt.set_camera()
+            if world == 1:
+                pt.render_frame_host(WIDTH, HEIGHT, True, rgb_np, yuv_np)
+                d2h = rgb_np.nbytes + yuv_np.nbytes
+            else:
+                rr.render_frame(plan, queue, rank, world)
+                if rank == 0:
+                    rgb_host.view(-1).copy_(rr.rgb, non_blocking=True)
+                    yuv_host.copy_(rr.yuv, non_blocking=True)
+                    d2h = rgb_np.nbytes + yuv_np.nbytes
+                torch.cuda.synchronize(device)
+            barrier()
+            return time.perf_counter() - t0
+
+        e2e_step()
+        secs = [e2e_step() for _ in range(args.steps)]
+        tsum = sum(secs)
+        if world > 1:
+            tt = torch.tensor([tsum], dtype=torch.float64, device=device)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tsum = float(tt[0])
+        if world > 1:
+            pt.bind_framebuffer(rr.rgb.data_ptr(), rr.yuv.data_ptr(), WIDTH, HEIGHT)
+        e2e = {"value": samples_per_step * args.steps / tsum / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1000.0 * tsum / args.steps}
+
+    if rank == 0:
+        peaks = measured_peaks()
+        n_kernel_launches = max(1, launches)
+        kernel_ms = total_ms / (n_kernel_launches if world == 1 else args.steps)  # N=1: one launch per step
+        rays_per_launch = rays / (n_kernel_launches if world == 1 else args.steps * world)
+        abytes = BYTES_PER_RAY(per_ray["box"], per_ray["tri"]) * rays_per_launch
+        aflops = FLOPS_PER_RAY(per_ray["box"], per_ray["tri"]) * rays_per_launch
+        sm_mhz = (clocks or {}).get("sm_mhz") or peaks["sm_max_mhz"]
+        fp32_peak_max = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+        roofline = {"bound": "hbm", "achieved": abytes / (kernel_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": abytes / (kernel_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "kernel": "pt_persistent_kernel" if args.kernel == "persistent" else "pt_direct_kernel",
+                    "peak_source": peaks["source"], "algorithmic_bytes_per_ray": BYTES_PER_RAY(per_ray["box"], per_ray["tri"]),
+                    "note": "algorithmic bytes are node/triangle fetches served by L1/L2 on this 1.5 MB scene; the binding roof is FP32 issue (roofline_fp32)"}
+        roofline_fp32 = {"bound": "fp32", "achieved": aflops / (kernel_ms / 1e3) / 1e12, "peak": fp32_peak_max, "unit": "TFLOP/s",
+                         "frac": aflops / (kernel_ms / 1e3) / 1e12 / fp32_peak_max, "peak_at_sustained_clock": 148 * 128 * 2 * sm_mhz * 1e6 / 1e12,
+                         "algorithmic_flops_per_ray": FLOPS_PER_RAY(per_ray["box"], per_ray["tri"])}
+        line = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "reference model cornell_duck (converted fixture), fixed XORWOW seeds",
+                "config": {"workload": WORKLOAD if spp == SPP else WORKLOAD + f" [spp overridden to {spp}]", "kernel": args.kernel, "l2": "flushed between steps (256 MiB write)",
+                           "parallelism": "1 GPU" if world == 1 else f"image tiles {tw}x{th}, dynamic claims of {claim}, NCCL reduce gather",
+                           "rng": "XORWOW per pixel, reference stream order"},
+                "mrays_per_s": mrays, "rays_per_sample": rays / (samples_per_step * args.steps), "per_ray": per_ray, "wall_s_timed_region": t_wall,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_fp32": roofline_fp32}
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_sample(host_cores())
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if world == 1 and not args.no_ref_gpu:
+            pt.close()
+            line["ref_gpu"] = gpu_reference_sample()
+        print(json.dumps(line), flush=True)
+    if queue is not None:
+        barrier()
+        queue.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

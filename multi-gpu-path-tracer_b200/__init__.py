@@ -1,0 +1,28 @@
+"""multi-gpu-path-tracer_b200 — B200-native path-tracing core behind the reference's device API.
+
+Layout
+    csrc/core   CUDA kernels (sm_100a) + the C ABI of include/ptcore.h  -> _lib/libptcore.so
+    csrc/host   C++ mirror of the reference's host API (DevicePathTracer, RenderManager, ...)
+    capi.py     ctypes binding (plumbing for tests / bench / multi-rank scheduling)
+    scenes.py   synthetic scene generators for the BASELINE configs without a model file
+    sched.py    one-process-per-GPU dynamic tile scheduling + NCCL framebuffer gather
+
+The directory name is the project's; import it as `import ptb200` (shim at the repo root) or
+`importlib.import_module("multi-gpu-path-tracer_b200")`.
+"""
+from .capi import (  # noqa: F401
+    DEFAULT_CAMERA, MAT_DTYPE, PT_KERNEL_DIRECT, PT_KERNEL_PERSISTENT, PT_MAT_DIELECTRIC, PT_MAT_DIFFUSE_LIGHT, PT_MAT_LAMBERTIAN,
+    PT_MAT_METAL, PT_MAT_UNIVERSAL, PT_OPT_BLOCKS_PER_SM, PT_OPT_BVH_LEAF_MAX, PT_OPT_COUNT_TESTS, PT_OPT_KERNEL, PT_OPT_SLICE_SPP,
+    PathTracer, PtCamera, PtError, PtMaterial, PtSceneDesc, PtStats, PtTexture, PtTile, Scene, TileQueue, LIB_PATH,
+    load_library, load_scene_file, make_camera, write_ppm,
+)
+
+__all__ = [n for n in dir() if not n.startswith("_")]
+
+
+def __getattr__(name):
+    # torch-dependent / heavier submodules are imported on first use: ptb200.sched, ptb200.scenes
+    if name in ("sched", "scenes"):
+        import importlib
+        return importlib.import_module(f"{__name__}.{name}")
+    raise AttributeError(name)

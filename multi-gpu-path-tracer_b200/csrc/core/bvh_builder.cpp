@@ -1,0 +1,356 @@
+// bvh_builder.cpp — see bvh_builder.h.
+#include "bvh_builder.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+namespace ptc {
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() {
+        for (int k = 0; k < 3; k++) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; }
+    }
+    void grow(const float *l, const float *h) {
+        for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], l[k]); hi[k] = std::max(hi[k], h[k]); }
+    }
+    void grow(const Box &b) { grow(b.lo, b.hi); }
+    float half_area() const {
+        float e[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+        if (e[0] < 0 || e[1] < 0 || e[2] < 0) return 0.f;
+        return e[0] * e[1] + e[1] * e[2] + e[2] * e[0];
+    }
+};
+
+struct TmpNode {
+    Box box;
+    int32_t left = -1, right = -1;  // children (TmpNode indices) or -1
+    int32_t first = 0, count = 0;   // range in `order`
+};
+
+struct Builder {
+    const std::vector<PrimBounds> &pb;
+    BvhBuildOptions opt;
+    std::vector<int32_t> order;
+    std::vector<float> cent;  // 3 per prim
+    std::vector<TmpNode> tmp;
+    std::vector<float> sweepArea;
+    uint32_t maxDepth = 0;
+
+    Builder(const std::vector<PrimBounds> &b, const BvhBuildOptions &o) : pb(b), opt(o) {}
+
+    Box rangeBox(int32_t first, int32_t count, Box *centBox) const {
+        Box b;
+        b.reset();
+        if (centBox) centBox->reset();
+        for (int32_t i = 0; i < count; i++) {
+            int32_t id = order[(size_t)first + (size_t)i];
+            b.grow(pb[(size_t)id].lo, pb[(size_t)id].hi);
+            if (centBox) {
+                const float *c = &cent[(size_t)id * 3];
+                centBox->grow(c, c);
+            }
+        }
+        return b;
+    }
+
+    // Returns split position in `order` (first < mid < first+count) or -1 for "make a leaf".
+    int32_t findSplit(int32_t first, int32_t count, const Box &box, const Box &cbox, bool mustSplit, bool forceMedian) {
+        const float parentArea = std::max(box.half_area(), 1e-30f);
+        const float leafCost = opt.intersect_cost * (float)count;
+        float bestCost = std::numeric_limits<float>::infinity();
+        int bestAxis = -1;
+        int32_t bestMid = -1;
+        float bestPlane = 0.f;
+        bool bestIsSweep = false;
+
+        if (!forceMedian) {
+            if (count <= 64) {
+                // exact sweep over centroid-sorted order, all three axes
+                std::vector<int32_t> ids(order.begin() + first, order.begin() + first + count);
+                if ((int32_t)sweepArea.size() < count) sweepArea.resize((size_t)count);
+                for (int axis = 0; axis < 3; axis++) {
+                    if (!(cbox.hi[axis] > cbox.lo[axis])) continue;
+                    std::stable_sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) { return cent[(size_t)a * 3 + axis] < cent[(size_t)b * 3 + axis]; });
+                    Box acc;
+                    acc.reset();
+                    for (int32_t i = count - 1; i > 0; i--) {
+                        acc.grow(pb[(size_t)ids[(size_t)i]].lo, pb[(size_t)ids[(size_t)i]].hi);
+                        sweepArea[(size_t)i] = acc.half_area();
+                    }
+                    acc.reset();
+                    for (int32_t i = 1; i < count; i++) {
+                        acc.grow(pb[(size_t)ids[(size_t)i - 1]].lo, pb[(size_t)ids[(size_t)i - 1]].hi);
+                        float cost = opt.traversal_cost + opt.intersect_cost * (acc.half_area() * (float)i + sweepArea[(size_t)i] * (float)(count - i)) / parentArea;
+                        if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestMid = i; bestIsSweep = true; }
+                    }
+                }
+            } else {
+                const int B = std::max(4, std::min(opt.bins, 64));
+                for (int axis = 0; axis < 3; axis++) {
+                    float lo = cbox.lo[axis], hi = cbox.hi[axis];
+                    if (!(hi > lo)) continue;
+                    Box bins[64];
+                    int32_t cnt[64];
+                    for (int b = 0; b < B; b++) { bins[b].reset(); cnt[b] = 0; }
+                    float scale = (float)B / (hi - lo);
+                    for (int32_t i = 0; i < count; i++) {
+                        int32_t id = order[(size_t)first + (size_t)i];
+                        int b = (int)((cent[(size_t)id * 3 + axis] - lo) * scale);
+                        b = std::max(0, std::min(B - 1, b));
+                        bins[b].grow(pb[(size_t)id].lo, pb[(size_t)id].hi);
+                        cnt[b]++;
+                    }
+                    float rightArea[64];
+                    int32_t rightCnt[64];
+                    Box acc;
+                    acc.reset();
+                    int32_t c = 0;
+                    for (int b = B - 1; b > 0; b--) {
+                        acc.grow(bins[b]);
+                        c += cnt[b];
+                        rightArea[b] = acc.half_area();
+                        rightCnt[b] = c;
+                    }
+                    acc.reset();
+                    c = 0;
+                    for (int b = 1; b < B; b++) {
+                        acc.grow(bins[b - 1]);
+                        c += cnt[b - 1];
+                        if (c == 0 || rightCnt[b] == 0) continue;
+                        float cost = opt.traversal_cost + opt.intersect_cost * (acc.half_area() * (float)c + rightArea[b] * (float)rightCnt[b]) / parentArea;
+                        if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestPlane = lo + (float)b / scale; bestMid = c; bestIsSweep = false; }
+                    }
+                }
+            }
+        }
+
+        bool wantLeaf = !mustSplit && (bestAxis < 0 || bestCost >= leafCost);
+        if (wantLeaf) return -1;
+
+        if (bestAxis >= 0 && bestIsSweep) {
+            int axis = bestAxis;
+            std::stable_sort(order.begin() + first, order.begin() + first + count,
+                             [&](int32_t a, int32_t b) { return cent[(size_t)a * 3 + axis] < cent[(size_t)b * 3 + axis]; });
+            return first + bestMid;
+        }
+        if (bestAxis >= 0) {
+            int axis = bestAxis;
+            float lo = cbox.lo[axis], hi = cbox.hi[axis];
+            const int B = std::max(4, std::min(opt.bins, 64));
+            float scale = (float)B / (hi - lo);
+            int planeBin = (int)std::lround((bestPlane - lo) * scale);
+            auto mid = std::partition(order.begin() + first, order.begin() + first + count, [&](int32_t id) {
+                int b = (int)((cent[(size_t)id * 3 + axis] - lo) * scale);
+                b = std::max(0, std::min(B - 1, b));
+                return b < planeBin;
+            });
+            int32_t m = (int32_t)(mid - order.begin());
+            if (m > first && m < first + count) return m;
+        }
+        // median fallback: largest centroid extent, split by count
+        int axis = 0;
+        for (int k = 1; k < 3; k++)
+            if (cbox.hi[k] - cbox.lo[k] > cbox.hi[axis] - cbox.lo[axis]) axis = k;
+        int32_t m = first + count / 2;
+        std::nth_element(order.begin() + first, order.begin() + (m - 0), order.begin() + first + count,
+                         [&](int32_t a, int32_t b) { return cent[(size_t)a * 3 + axis] < cent[(size_t)b * 3 + axis]; });
+        return m;
+    }
+
+    void run() {
+        const size_t n = pb.size();
+        order.resize(n);
+        std::iota(order.begin(), order.end(), 0);
+        cent.resize(n * 3);
+        for (size_t i = 0; i < n; i++)
+            for (int k = 0; k < 3; k++) cent[i * 3 + k] = 0.5f * (pb[i].lo[k] + pb[i].hi[k]);
+        tmp.reserve(n ? 2 * n : 1);
+        struct Work { int32_t node; uint32_t depth; };
+        std::vector<Work> stack;
+        TmpNode root;
+        root.first = 0;
+        root.count = (int32_t)n;
+        Box cb;
+        root.box = rangeBox(0, (int32_t)n, &cb);
+        tmp.push_back(root);
+        stack.push_back({0, 1});
+        const int leafMax = std::max(1, std::min(opt.leaf_max, kMaxLeafPrims));
+        while (!stack.empty()) {
+            Work w = stack.back();
+            stack.pop_back();
+            maxDepth = std::max(maxDepth, w.depth);
+            int32_t first = tmp[(size_t)w.node].first, count = tmp[(size_t)w.node].count;
+            if (count <= 1) continue;
+            Box cbox;
+            Box box = rangeBox(first, count, &cbox);
+            bool mustSplit = count > leafMax;
+            // keep the tree shallow enough for the device stack: once deep, split by count
+            uint32_t remaining = 1;
+            while ((1u << remaining) * (uint32_t)leafMax < (uint32_t)count && remaining < 31) remaining++;
+            bool forceMedian = w.depth + remaining + 2 >= (uint32_t)kMaxTraversalDepth;
+            int32_t mid = findSplit(first, count, box, cbox, mustSplit, forceMedian);
+            if (mid < 0) continue;
+            TmpNode l, r;
+            l.first = first; l.count = mid - first;
+            r.first = mid; r.count = first + count - mid;
+            l.box = rangeBox(l.first, l.count, nullptr);
+            r.box = rangeBox(r.first, r.count, nullptr);
+            int32_t li = (int32_t)tmp.size();
+            tmp.push_back(l);
+            int32_t ri = (int32_t)tmp.size();
+            tmp.push_back(r);
+            tmp[(size_t)w.node].left = li;
+            tmp[(size_t)w.node].right = ri;
+            stack.push_back({ri, w.depth + 1});
+            stack.push_back({li, w.depth + 1});
+        }
+    }
+};
+
+inline int32_t leaf_ref(int32_t first, int32_t count) { return ~((first << kLeafCountBits) | (count - 1)); }
+
+}  // namespace
+
+BvhBuildResult build_bvh(const std::vector<PrimBounds> &bounds, const BvhBuildOptions &opt) {
+    auto t0 = std::chrono::high_resolution_clock::now();
+    BvhBuildResult out;
+    const float inf = std::numeric_limits<float>::infinity();
+    auto emptyChild = [&](FlatNode &n, int side) {
+        n.bx[side * 2] = n.by[side * 2] = n.bz[side * 2] = inf;
+        n.bx[side * 2 + 1] = n.by[side * 2 + 1] = n.bz[side * 2 + 1] = -inf;
+    };
+    if (bounds.empty()) {
+        FlatNode n{};
+        emptyChild(n, 0);
+        emptyChild(n, 1);
+        n.left = n.right = leaf_ref(0, 1);  // never entered
+        out.nodes.push_back(n);
+        out.depth = 1;
+        return out;
+    }
+    Builder b(bounds, opt);
+    b.run();
+    out.prim_order = b.order;
+    out.depth = b.maxDepth;
+
+    // flatten: inner TmpNodes -> FlatNodes in DFS order; leaves become child refs
+    std::vector<int32_t> flatIndex(b.tmp.size(), -1);
+    struct Item { int32_t tmp; };
+    std::vector<int32_t> dfs;
+    if (b.tmp[0].left < 0) {
+        // single-leaf scene (possibly more than leaf_max prims if they are all coincident): chain it
+        FlatNode n{};
+        const TmpNode &t = b.tmp[0];
+        int32_t cnt = std::min<int32_t>(t.count, kMaxLeafPrims);
+        n.bx[0] = t.box.lo[0]; n.bx[1] = t.box.hi[0];
+        n.by[0] = t.box.lo[1]; n.by[1] = t.box.hi[1];
+        n.bz[0] = t.box.lo[2]; n.bz[1] = t.box.hi[2];
+        emptyChild(n, 1);
+        n.left = leaf_ref(t.first, cnt);
+        n.right = leaf_ref(0, 1);
+        out.nodes.push_back(n);
+        out.n_leaves = 1;
+        out.sah_cost = opt.intersect_cost * (double)t.count;
+    } else {
+        dfs.push_back(0);
+        while (!dfs.empty()) {
+            int32_t ti = dfs.back();
+            dfs.pop_back();
+            flatIndex[(size_t)ti] = (int32_t)out.nodes.size();
+            out.nodes.emplace_back();
+            const TmpNode &t = b.tmp[(size_t)ti];
+            if (b.tmp[(size_t)t.right].left >= 0) dfs.push_back(t.right);
+            if (b.tmp[(size_t)t.left].left >= 0) dfs.push_back(t.left);
+        }
+        const double rootArea = std::max((double)b.tmp[0].box.half_area(), 1e-30);
+        for (size_t ti = 0; ti < b.tmp.size(); ti++) {
+            if (flatIndex[ti] < 0) continue;
+            const TmpNode &t = b.tmp[ti];
+            FlatNode &n = out.nodes[(size_t)flatIndex[ti]];
+            const TmpNode *ch[2] = {&b.tmp[(size_t)t.left], &b.tmp[(size_t)t.right]};
+            int32_t ci[2] = {t.left, t.right};
+            int32_t refs[2];
+            for (int s = 0; s < 2; s++) {
+                n.bx[s * 2] = ch[s]->box.lo[0]; n.bx[s * 2 + 1] = ch[s]->box.hi[0];
+                n.by[s * 2] = ch[s]->box.lo[1]; n.by[s * 2 + 1] = ch[s]->box.hi[1];
+                n.bz[s * 2] = ch[s]->box.lo[2]; n.bz[s * 2 + 1] = ch[s]->box.hi[2];
+                if (ch[s]->left >= 0) {
+                    refs[s] = flatIndex[(size_t)ci[s]];
+                    out.sah_cost += opt.traversal_cost * (double)ch[s]->box.half_area() / rootArea;
+                } else {
+                    refs[s] = leaf_ref(ch[s]->first, ch[s]->count);
+                    out.n_leaves++;
+                    out.sah_cost += opt.intersect_cost * (double)ch[s]->count * (double)ch[s]->box.half_area() / rootArea;
+                }
+            }
+            n.left = refs[0];
+            n.right = refs[1];
+            n.pad0 = n.pad1 = 0;
+        }
+        out.sah_cost += opt.traversal_cost;
+    }
+    auto t1 = std::chrono::high_resolution_clock::now();
+    out.build_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    return out;
+}
+
+const char *validate_bvh(const BvhBuildResult &bvh, const std::vector<PrimBounds> &bounds) {
+    const size_t n = bounds.size();
+    if (bvh.nodes.empty()) return "no nodes";
+    if (n == 0) return "";
+    if (bvh.prim_order.size() != n) return "prim_order size mismatch";
+    std::vector<uint8_t> seenPrim(n, 0), seenPos(n, 0), seenNode(bvh.nodes.size(), 0);
+    for (int32_t id : bvh.prim_order) {
+        if (id < 0 || (size_t)id >= n) return "prim_order entry out of range";
+        if (seenPrim[(size_t)id]) return "primitive listed twice";
+        seenPrim[(size_t)id] = 1;
+    }
+    struct W { int32_t node; uint32_t depth; float lo[3], hi[3]; };
+    std::vector<W> st;
+    const float inf = std::numeric_limits<float>::infinity();
+    st.push_back({0, 1, {-inf, -inf, -inf}, {inf, inf, inf}});
+    uint32_t depth = 0;
+    while (!st.empty()) {
+        W w = st.back();
+        st.pop_back();
+        if (w.node < 0 || (size_t)w.node >= bvh.nodes.size()) return "node ref out of range";
+        if (seenNode[(size_t)w.node]) return "node reached twice";
+        seenNode[(size_t)w.node] = 1;
+        depth = std::max(depth, w.depth);
+        const FlatNode &nd = bvh.nodes[(size_t)w.node];
+        for (int s = 0; s < 2; s++) {
+            float lo[3] = {nd.bx[s * 2], nd.by[s * 2], nd.bz[s * 2]}, hi[3] = {nd.bx[s * 2 + 1], nd.by[s * 2 + 1], nd.bz[s * 2 + 1]};
+            int32_t ref = s ? nd.right : nd.left;
+            if (lo[0] > hi[0]) continue;  // absent child
+            for (int k = 0; k < 3; k++)
+                if (lo[k] < w.lo[k] || hi[k] > w.hi[k]) return "child box not inside parent box";
+            if (ref >= 0) {
+                W c{ref, w.depth + 1, {lo[0], lo[1], lo[2]}, {hi[0], hi[1], hi[2]}};
+                st.push_back(c);
+            } else {
+                int32_t v = ~ref, first = v >> kLeafCountBits, count = (v & (kMaxLeafPrims - 1)) + 1;
+                if (first < 0 || (size_t)first + (size_t)count > n) return "leaf range out of bounds";
+                for (int32_t i = 0; i < count; i++) {
+                    if (seenPos[(size_t)first + (size_t)i]) return "leaf ranges overlap";
+                    seenPos[(size_t)first + (size_t)i] = 1;
+                    const PrimBounds &p = bounds[(size_t)bvh.prim_order[(size_t)first + (size_t)i]];
+                    for (int k = 0; k < 3; k++)
+                        if (p.lo[k] < lo[k] || p.hi[k] > hi[k]) return "primitive not inside its leaf box";
+                }
+            }
+        }
+    }
+    for (size_t i = 0; i < n; i++)
+        if (!seenPos[i]) return "primitive not reachable from the root";
+    if (depth > (uint32_t)kMaxTraversalDepth) return "tree deeper than the device stack";
+    return "";
+}
+
+}  // namespace ptc

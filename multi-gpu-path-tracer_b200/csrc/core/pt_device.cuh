@@ -1,0 +1,543 @@
+// pt_device.cuh — device-side building blocks of the path-tracing core (sm_100a).
+//
+// Every function cites the reference lines whose RESULT it must reproduce
+// (paths relative to /root/reference).  The arithmetic keeps the reference's expression
+// shapes (operand order, float vs double literals, rsqrtf / sqrtf / sinf / cosf / IEEE
+// division) so that nvcc contracts and rounds it the way it does for the reference's own
+// kernels; the data layout, traversal, scheduling and RNG-state handling are new.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+namespace ptc {
+
+#ifndef PT_M_PI
+#define PT_M_PI 3.14159265358979323846 /* M_PI as the reference sees it (double) */
+#endif
+
+// ----------------------------------------------------------------------------------------
+// device scene view (pointers into one bulk-uploaded blob, all 128-byte aligned)
+// ----------------------------------------------------------------------------------------
+struct TexDesc {
+    int32_t width, height;
+    uint32_t offset;  // first texel, in float4 units
+    uint32_t pad;
+};
+
+struct DevScene {
+    const float4 *nodes;   // 4 per node     (FlatNode, bvh_builder.h)
+    const float4 *prims;   // 3 per primitive in leaf order:
+                           //   triangle: (v0.xyz, e1.x) (e1.yz, e2.xy) (e2.z, -, kind=0, -)
+                           //   sphere  : (c.xyz, r)     (-,-,-,-)      (-, -, kind=1, -)
+    const float4 *shade;   // 2 per primitive: (uv0, uv1) (uv2, material index, original primitive index)
+    const float4 *mats;    // 3 per material : (type, base.rgb) (emis.rgb, base_tex) (emis_tex, fuzz, ior, -)
+    const TexDesc *texs;
+    const float4 *texels;  // (r,g,b,-) already scaled by 1/255 exactly as Texture.h:45-46 does
+    const float4 *lights;  // 3 per light triangle: (v0.xyz, area) (v1.xyz, -) (v2.xyz, -), scene order
+    int32_t n_lights;
+    int32_t n_prims;
+    double light_pick_scale;  // (n_lights - 1) + 0.999999, hitable_list.h:24
+    float light_weight;       // 1.0f / n_lights, hitable_list.h:17
+    int32_t pad;
+};
+
+struct CamParams {  // camera.h:21-36, evaluated once per set_camera by a 1-thread device kernel
+    float3 origin, lower_left_corner, horizontal, vertical;
+};
+
+constexpr int kMaxInlineTiles = 48;
+struct TileList {
+    int32_t n;
+    int32_t ox[kMaxInlineTiles], oy[kMaxInlineTiles], w[kMaxInlineTiles], h[kMaxInlineTiles];
+    uint32_t first_item[kMaxInlineTiles + 1];  // prefix sums of 32 * ceil(w/8) * ceil(h/4)
+};
+
+struct DevCounters {
+    unsigned long long rays, box_tests, tri_tests, light_tests, samples;
+};
+
+struct RenderParams {
+    DevScene scene;
+    CamParams cam;
+    uint32_t width, height, spp, depth;
+    uint8_t *fb_rgb, *fb_yuv;
+    uint32_t *work_counter;
+    DevCounters *counters;
+    TileList tiles;
+};
+
+// ----------------------------------------------------------------------------------------
+// float3 helpers with the expression shapes of helper_math.h
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float b) { return f3(a.x * b, a.y * b, a.z * b); }
+__device__ __forceinline__ float3 operator*(float b, float3 a) { return f3(b * a.x, b * a.y, b * a.z); }
+__device__ __forceinline__ float3 operator/(float3 a, float b) { return f3(a.x / b, a.y / b, a.z / b); }  // helper_math.h:1015-1018
+__device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }    // :1266-1269
+__device__ __forceinline__ float3 cross(float3 a, float3 b) {                                             // :1461-1464
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float length(float3 v) { return sqrtf(dot(v, v)); }                            // :1309-1312
+__device__ __forceinline__ float3 normalize(float3 v) {                                                   // :1327-1331
+    float invLen = rsqrtf(dot(v, v));
+    return v * invLen;
+}
+
+// ----------------------------------------------------------------------------------------
+// cuRAND XORWOW, subsequence 0 / offset 0 (curand_kernel.h:772-797, 863-874; curand_uniform.h:69-72).
+// The reference keeps a 48-byte curandState per framebuffer pixel in global memory
+// (src/DevicePathTracer.h:352) initialised by render_init (:46-55) and never written back (:80);
+// the seed only depends on the pixel index, so the state is rebuilt in registers instead.
+// ----------------------------------------------------------------------------------------
+struct Rng {
+    uint32_t d, v0, v1, v2, v3, v4;
+};
+__device__ __forceinline__ void rng_init(Rng &s, unsigned long long seed) {
+    uint32_t s0 = ((uint32_t)seed) ^ 0xaad26b49U;
+    uint32_t s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddU;
+    uint32_t t0 = 1099087573U * s0;
+    uint32_t t1 = 2591861531U * s1;
+    s.d = 6615241U + t1 + t0;
+    s.v0 = 123456789U + t0;
+    s.v1 = 362436069U ^ t0;
+    s.v2 = 521288629U + t1;
+    s.v3 = 88675123U ^ t1;
+    s.v4 = 5783321U + t0;
+}
+__device__ __forceinline__ uint32_t rng_next(Rng &s) {
+    uint32_t t = s.v0 ^ (s.v0 >> 2);
+    s.v0 = s.v1;
+    s.v1 = s.v2;
+    s.v2 = s.v3;
+    s.v3 = s.v4;
+    s.v4 = (s.v4 ^ (s.v4 << 4)) ^ (t ^ (t << 1));
+    s.d += 362437U;
+    return s.v4 + s.d;
+}
+__device__ __forceinline__ float rng_uniform(Rng &s) {
+    // x * 2^-32 + 2^-33: the product is exact, so fused or not gives the same float
+    return (float)rng_next(s) * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+}
+
+// ----------------------------------------------------------------------------------------
+// comparisons against the reference's double literals, folded to float.
+// For a float x:  x <  1e-8  (double)  <=>  x <  kDetEpsUp   (smallest float >= 1e-8)
+//                 x > -1e-8  (double)  <=>  x > -kDetEpsUp
+//                 x > 0.0001 (double)  <=>  x >  0.0001f      (float(0.0001) < 0.0001)
+// (exhaustively checked on the host in tests/test_host_logic.py via the oracle's helpers)
+// ----------------------------------------------------------------------------------------
+#define PT_DET_EPS_UP 1.00000008274037e-08f
+
+// (float)(1.0 / (double)x) == IEEE float division 1.0f / x for every normal x whose
+// reciprocal is normal: the double quotient can never sit within 2^-53 of a float rounding
+// boundary (x * midpoint is a 49-bit product, so it is either exactly a power of two or at
+// least 2^-49 away in relative terms).  triangle.h:84.
+__device__ __forceinline__ float rcp_like_double(float x) { return __fdiv_rn(1.0f, x); }
+
+// cosine / M_PI with the reference's double division (material.h:90, pdf.h:21)
+__device__ __forceinline__ float div_pi(float c) { return (float)((double)c / PT_M_PI); }
+
+// ----------------------------------------------------------------------------------------
+// primitive tests
+// ----------------------------------------------------------------------------------------
+struct Hit {
+    float t;      // FLT_MAX when nothing was hit
+    float u, v;   // barycentrics of the accepted triangle hit
+    int32_t prim; // leaf-order primitive position, -1 for a miss
+};
+
+// triangle.h:63-113 with e1/e2 precomputed (the same float subtractions the reference redoes per test).
+// Branch-free: every lane evaluates the whole test and folds the reference's early-outs into one predicate;
+// the NaN behaviour of the original comparisons (u<0||u>1 etc. are false for NaN) is preserved.
+__device__ __forceinline__ bool triangle_test(float3 v0, float3 e1, float3 e2, float3 o, float3 d, float tmin, float tmax,
+                                              float &t_out, float &u_out, float &v_out) {
+    float3 pvec = cross(d, e2);
+    float det = dot(e1, pvec);
+    float inv_det = rcp_like_double(det);
+    float3 tvec = o - v0;
+    float u = dot(tvec, pvec) * inv_det;
+    float3 qvec = cross(tvec, e1);
+    float v = dot(d, qvec) * inv_det;
+    float t = dot(e2, qvec) * inv_det;
+    bool reject = (det < PT_DET_EPS_UP && det > -PT_DET_EPS_UP) | (u < 0) | (u > 1) | (v < 0) | (u + v > 1);
+    bool ok = !reject & (t < tmax) & (t > tmin);
+    t_out = t;
+    u_out = u;
+    v_out = v;
+    return ok;
+}
+
+// sphere.h:21-50 (double-precision spots kept: b = 2.0*dot, roots divided by 2.0*a)
+__device__ __forceinline__ bool sphere_test(float3 center, float radius, float3 o, float3 d, float tmin, float tmax, float &t_out) {
+    float3 oc = o - center;
+    float a = dot(d, d);
+    float b = (float)(2.0 * dot(oc, d));
+    float c = dot(oc, oc) - radius * radius;
+    float discriminant = b * b - 4 * a * c;
+    float sq = sqrtf(discriminant);
+    float t0 = (float)((-b - sq) / (2.0 * a));
+    float t1 = (float)((-b + sq) / (2.0 * a));
+    bool ok0 = (discriminant > 0) & (t0 < tmax) & (t0 > tmin);
+    bool ok1 = (discriminant > 0) & (t1 < tmax) & (t1 > tmin);
+    t_out = ok0 ? t0 : t1;
+    return ok0 | ok1;
+}
+
+// ----------------------------------------------------------------------------------------
+// closest hit: replaces BVH::hit (bvh.h:178-246) + aabb::hit (aabb.h:38-66).
+// Same result (closest accepted triangle::hit over all primitives), different walk:
+// t-culled slab tests on both children of a 64-byte node, near child first, stack of far
+// children in per-thread local memory, leaves of <= 8 primitives fetched as 3 x LDG.128.
+// ----------------------------------------------------------------------------------------
+constexpr int kStackSize = 48;
+
+template <bool SPHERES, bool COUNT>
+__device__ __forceinline__ Hit closest_hit(const DevScene &sc, float3 o, float3 d, float tmin, uint32_t &n_box, uint32_t &n_tri) {
+    Hit best;
+    best.t = FLT_MAX;
+    best.u = best.v = 0.f;
+    best.prim = -1;
+
+    const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const float3 oinv = f3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+    const float kSlack = 1.0000004f;  // boxes are padded on the host; this covers the fma rounding of the slab distances
+
+    int32_t stack[kStackSize];
+    int sp = 0;
+    int32_t node = 0;
+    for (;;) {
+        if (node >= 0) {
+            const float4 bx = __ldg(&sc.nodes[node * 4 + 0]);
+            const float4 by = __ldg(&sc.nodes[node * 4 + 1]);
+            const float4 bz = __ldg(&sc.nodes[node * 4 + 2]);
+            const int4 refs = __ldg(reinterpret_cast<const int4 *>(&sc.nodes[node * 4 + 3]));
+            if (COUNT) n_box += 2;
+            // left
+            float lx0 = fmaf(bx.x, inv.x, oinv.x), lx1 = fmaf(bx.y, inv.x, oinv.x);
+            float ly0 = fmaf(by.x, inv.y, oinv.y), ly1 = fmaf(by.y, inv.y, oinv.y);
+            float lz0 = fmaf(bz.x, inv.z, oinv.z), lz1 = fmaf(bz.y, inv.z, oinv.z);
+            float ln = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), tmin));
+            float lf = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), best.t));
+            // right
+            float rx0 = fmaf(bx.z, inv.x, oinv.x), rx1 = fmaf(bx.w, inv.x, oinv.x);
+            float ry0 = fmaf(by.z, inv.y, oinv.y), ry1 = fmaf(by.w, inv.y, oinv.y);
+            float rz0 = fmaf(bz.z, inv.z, oinv.z), rz1 = fmaf(bz.w, inv.z, oinv.z);
+            float rn = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), tmin));
+            float rf = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), best.t));
+            bool hl = ln <= lf * kSlack;
+            bool hr = rn <= rf * kSlack;
+            if (hl & hr) {
+                bool leftFirst = ln <= rn;
+                int32_t nearRef = leftFirst ? refs.x : refs.y;
+                int32_t farRef = leftFirst ? refs.y : refs.x;
+                stack[sp++] = farRef;
+                node = nearRef;
+                continue;
+            }
+            if (hl) { node = refs.x; continue; }
+            if (hr) { node = refs.y; continue; }
+        } else {
+            const int32_t v = ~node;
+            const int32_t first = v >> 3;
+            const int32_t count = (v & 7) + 1;
+            for (int32_t i = 0; i < count; i++) {
+                const int32_t k = first + i;
+                const float4 q0 = __ldg(&sc.prims[k * 3 + 0]);
+                const float4 q1 = __ldg(&sc.prims[k * 3 + 1]);
+                const float4 q2 = __ldg(&sc.prims[k * 3 + 2]);
+                if (COUNT) n_tri += 1;
+                if (SPHERES && __float_as_int(q2.z) == 1) {
+                    float t;
+                    if (sphere_test(f3(q0.x, q0.y, q0.z), q0.w, o, d, tmin, best.t, t)) {
+                        best.t = t;
+                        best.u = best.v = 0.f;
+                        best.prim = k;
+                    }
+                } else {
+                    float t, u, w;
+                    if (triangle_test(f3(q0.x, q0.y, q0.z), f3(q0.w, q1.x, q1.y), f3(q1.z, q1.w, q2.x), o, d, tmin, best.t, t, u, w)) {
+                        best.t = t;
+                        best.u = u;
+                        best.v = w;
+                        best.prim = k;
+                    }
+                }
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return best;
+}
+
+// ----------------------------------------------------------------------------------------
+// shading pieces
+// ----------------------------------------------------------------------------------------
+struct Onb {
+    float3 u, v, w;
+};
+__device__ __forceinline__ Onb make_onb(float3 n) {  // onb.h:8-13
+    Onb o;
+    o.w = normalize(n);
+    float3 a = fabsf(o.w.x) > 0.9f ? f3(0.0f, 1.0f, 0.0f) : f3(1.0f, 0.0f, 0.0f);
+    o.v = normalize(cross(o.w, a));
+    o.u = cross(o.w, o.v);
+    return o;
+}
+__device__ __forceinline__ float3 onb_local(const Onb &o, float3 a) {  // onb.h:19-21
+    return a.x * o.u + a.y * o.v + a.z * o.w;
+}
+
+__device__ __forceinline__ float3 random_cosine_direction(Rng &rng) {  // helper_math.h:1519-1528 (2x factor is the reference's)
+    float r1 = rng_uniform(rng);
+    float r2 = rng_uniform(rng);
+    float z = sqrtf(1 - r2);
+    float phi = (float)(2 * PT_M_PI * r1);
+    float x = cosf(phi) * 2 * sqrtf(r2);
+    float y = sinf(phi) * 2 * sqrtf(r2);
+    return f3(x, y, z);
+}
+
+__device__ __forceinline__ float3 random_in_unit_sphere(Rng &rng) {  // helper_math.h:1504-1518, draw order x,y,z
+    float3 p;
+    do {
+        float a = rng_uniform(rng), b = rng_uniform(rng), c = rng_uniform(rng);
+        p = 2.0f * f3(a, b, c) - f3(1.0f, 1.0f, 1.0f);
+    } while (dot(p, p) >= 1.0f);
+    return p;
+}
+
+__device__ __forceinline__ float3 texture_value(const DevScene &sc, int tex, float u, float v) {  // Texture.h:30-70
+    const TexDesc td = sc.texs[tex];
+    if (td.height <= 0) return f3((float)242 / 255, (float)45 / 255, (float)27 / 255);
+    u = fmodf(u, 1.0f);
+    v = fmodf(v, 1.0f);
+    int i = (int)(u * td.width);
+    int j = (int)(v * td.height);
+    int x = i < 0 ? 0 : (i < td.width ? i : td.width - 1);
+    int y = j < 0 ? 0 : (j < td.height ? j : td.height - 1);
+    y = td.height - y;
+    if (y >= td.height) y = td.height - 1;  // the reference reads one row past the end here; defined as the last row
+    const float4 t = __ldg(&sc.texels[td.offset + (uint32_t)y * (uint32_t)td.width + (uint32_t)x]);
+    return f3(t.x, t.y, t.z);
+}
+
+// triangle::pdf_value (triangle.h:32-40) for one light triangle stored as v0/v1/v2/area
+__device__ __forceinline__ float light_pdf_value(float3 v0, float3 v1, float3 v2, float area, float3 o, float3 dir) {
+    float3 e1 = v1 - v0;
+    float3 e2 = v2 - v0;
+    float t, u, v;
+    if (!triangle_test(v0, e1, e2, o, dir, 0.001f, FLT_MAX, t, u, v)) return 0;
+    float3 normal = normalize(cross(e1, e2));
+    float distance_squared = t * t * dot(dir, dir);
+    float cosine = fabsf(dot(dir, normal) / length(dir));
+    return distance_squared / (cosine * area);
+}
+
+__device__ __forceinline__ float3 reflect3(float3 i, float3 n) { return i - 2.0f * n * dot(n, i); }  // helper_math.h:1429-1432
+__device__ __forceinline__ bool refract3(float3 v, float3 n, float ni_over_nt, float3 &refracted) {  // helper_math.cu:7-17
+    float3 uv = normalize(v);
+    float dt = dot(uv, n);
+    float discriminant = 1.0f - ni_over_nt * ni_over_nt * (1 - dt * dt);
+    if (discriminant > 0) {
+        refracted = ni_over_nt * (uv - n * dt) - n * sqrtf(discriminant);
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ float schlick(float cosine, float ref_idx) {  // material.h:10-14, pow5 by multiplication
+    float r0 = (1 - ref_idx) / (1 + ref_idx);
+    r0 = r0 * r0;
+    float x = 1 - cosine;
+    float x2 = x * x, x4 = x2 * x2, x5 = x4 * x;
+    return r0 + (1 - r0) * x5;
+}
+
+// camera.h:95-97
+__device__ __forceinline__ void camera_ray(const CamParams &c, float u, float v, float3 &o, float3 &d) {
+    o = c.origin;
+    d = c.lower_left_corner + u * c.horizontal + v * c.vertical - c.origin;
+}
+
+// quantiser + RGB8/I420 store: DevicePathTracer.h:98-119
+__device__ __forceinline__ void store_pixel(const RenderParams &p, int pixel_index, float3 col) {
+    float3 q = 255.99f * col / (float)p.spp * f3(1.f, 1.f, 1.f);
+    int r = min(255, __float2int_rz(q.x));
+    int g = min(255, __float2int_rz(q.y));
+    int b = min(255, __float2int_rz(q.z));
+    uint8_t *rgb = p.fb_rgb + 3 * (size_t)pixel_index;
+    rgb[0] = (uint8_t)r;
+    rgb[1] = (uint8_t)g;
+    rgb[2] = (uint8_t)b;
+    if (p.fb_yuv) {
+        p.fb_yuv[pixel_index] = (uint8_t)(((66 * r + 129 * g + 25 * b + 128) >> 8) + 16);
+        int blockRow = pixel_index / (int)p.width;
+        int blockCol = pixel_index % (int)p.width;
+        if (blockRow % 2 == 0 && blockCol % 2 == 0) {
+            int totalPixels = (int)(p.width * p.height);
+            int uvSize = totalPixels / 4;
+            int uvIndex = (blockRow / 2) * ((int)p.width / 2) + (blockCol / 2);
+            p.fb_yuv[totalPixels + uvIndex] = (uint8_t)(((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128);
+            p.fb_yuv[totalPixels + uvSize + uvIndex] = (uint8_t)(((112 * r - 94 * g - 18 * b + 128) >> 8) + 128);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// shade: everything camera::ray_color (camera.h:49-83) does between two BVH::hit calls.
+// Returns true when the path continues (o, d, att updated), false when it ended
+// (`contrib` then holds what the sample adds to the pixel).
+// ----------------------------------------------------------------------------------------
+template <bool SPHERES, bool RTOW, bool COUNT>
+__device__ __forceinline__ bool shade(const DevScene &sc, const Hit &h, float3 &o, float3 &d, float3 &att, Rng &rng, float3 &contrib,
+                                      uint32_t &n_light) {
+    if (h.prim < 0) {
+        contrib = f3(0.0f, 0.0f, 0.0f) * att;  // camera.h:79,109: background (0,0,0) * attenuation (NaN/inf propagate as in the reference)
+        return false;
+    }
+    const float4 q0 = __ldg(&sc.prims[h.prim * 3 + 0]);
+    const float4 q1 = __ldg(&sc.prims[h.prim * 3 + 1]);
+    const float4 q2 = __ldg(&sc.prims[h.prim * 3 + 2]);
+    const float4 s0 = __ldg(&sc.shade[h.prim * 2 + 0]);
+    const float4 s1 = __ldg(&sc.shade[h.prim * 2 + 1]);
+    const int mat = __float_as_int(s1.z);
+
+    const float3 p = o + h.t * d;  // ray.h:19
+    float3 normal;
+    float tu, tv;
+    if (SPHERES && __float_as_int(q2.z) == 1) {
+        normal = (p - f3(q0.x, q0.y, q0.z)) / q0.w;  // sphere.h:33
+        tu = tv = 0.f;
+    } else {
+        const float3 e1 = f3(q0.w, q1.x, q1.y), e2 = f3(q1.z, q1.w, q2.x);
+        normal = normalize(cross(e1, e2));  // triangle.h:103 — geometric, never flipped towards the ray
+        tu = (1 - h.u - h.v) * s0.x + h.u * s0.z + h.v * s1.x;  // triangle.h:106-107
+        tv = (1 - h.u - h.v) * s0.y + h.u * s0.w + h.v * s1.y;
+    }
+
+    const float4 m0 = __ldg(&sc.mats[mat * 3 + 0]);
+    const float4 m1 = __ldg(&sc.mats[mat * 3 + 1]);
+    const float4 m2 = __ldg(&sc.mats[mat * 3 + 2]);
+    const int type = __float_as_int(m0.x);
+    const float3 base = f3(m0.y, m0.z, m0.w);
+    const float3 emis = f3(m1.x, m1.y, m1.z);
+    const int base_tex = __float_as_int(m1.w);
+    const int emis_tex = __float_as_int(m2.x);
+
+    if (!RTOW || type == 4 /* PT_MAT_UNIVERSAL */) {
+        // UniversalMaterial::emitted / scatter, material.h:52-86
+        float3 emitted;
+        if (emis_tex >= 0) emitted = texture_value(sc, emis_tex, tu, tv) * emis * 50;
+        else emitted = emis * 50;
+        if (emitted.x > 0.0001f || emitted.y > 0.0001f || emitted.z > 0.0001f) {
+            contrib = att * emitted;  // camera.h:72-75
+            return false;
+        }
+        // material.h:67-69: scatter draws a cosine direction that camera.h:65 then overwrites — only the two draws matter
+        (void)rng_next(rng);
+        (void)rng_next(rng);
+        float3 attenuation = base;
+        if (base_tex >= 0) attenuation = attenuation * texture_value(sc, base_tex, tu, tv);  // material.h:71-75
+
+        // camera.h:62-66: mixture_pdf(light list, cosine).generate / .value — pdf.h:57-75
+        const Onb uvw = make_onb(normal);
+        float3 dir;
+        const bool have_lights = sc.n_lights > 0;
+        const float pick = rng_uniform(rng);
+        if (have_lights && pick < 0.5f) {
+            // hitable_list::random (hitable_list.h:23-26) -> triangle::random (triangle.h:41-47)
+            int index = (int)truncf((float)(rng_uniform(rng) * sc.light_pick_scale));
+            const float4 l0 = __ldg(&sc.lights[index * 3 + 0]);
+            const float4 l1 = __ldg(&sc.lights[index * 3 + 1]);
+            const float4 l2 = __ldg(&sc.lights[index * 3 + 2]);
+            float r1 = rng_uniform(rng);
+            float r2 = rng_uniform(rng);
+            float sqrt_r1 = sqrtf(r1);
+            float3 random_point = (1 - sqrt_r1) * f3(l0.x, l0.y, l0.z) + (sqrt_r1 * (1 - r2)) * f3(l1.x, l1.y, l1.z) + (sqrt_r1 * r2) * f3(l2.x, l2.y, l2.z);
+            dir = random_point - p;
+        } else {
+            dir = onb_local(uvw, random_cosine_direction(rng));  // cosine_pdf::generate, pdf.h:23-25
+        }
+        // hitable_list::pdf_value, hitable_list.h:16-22
+        float light_pdf = 0.0f;
+        for (int i = 0; i < sc.n_lights; i++) {
+            const float4 l0 = __ldg(&sc.lights[i * 3 + 0]);
+            const float4 l1 = __ldg(&sc.lights[i * 3 + 1]);
+            const float4 l2 = __ldg(&sc.lights[i * 3 + 2]);
+            if (COUNT) n_light += 1;
+            light_pdf += sc.light_weight * light_pdf_value(f3(l0.x, l0.y, l0.z), f3(l1.x, l1.y, l1.z), f3(l2.x, l2.y, l2.z), l0.w, p, dir);
+        }
+        // cosine_pdf::value, pdf.h:19-22 (w = normalize(normal) once more, as onb's constructor does)
+        const float3 ndir = normalize(dir);
+        float cosine = dot(ndir, uvw.w);
+        float cos_pdf = (cosine <= 0) ? 0 : div_pi(cosine);
+        float pdf_value = 0.5f * light_pdf + 0.5f * cos_pdf;  // pdf.h:63-65
+        // UniversalMaterial::scattering_pdf, material.h:88-91
+        float cosine2 = dot(normal, ndir);
+        float scattering_pdf = cosine2 < 0 ? 0 : div_pi(cosine2);
+        att = att * (attenuation * scattering_pdf / pdf_value);  // camera.h:69
+        o = p;
+        d = dir;
+        return true;
+    }
+    if (RTOW) {
+        if (type == 3 /* DIFFUSE_LIGHT */) {  // material.h:210-217 + builder-defined glue
+            contrib = att * emis;
+            return false;
+        }
+        float3 attenuation, sdir;
+        bool scattered = true;
+        if (type == 0 /* LAMBERTIAN */) {  // material.h:113-124
+            sdir = normal + random_in_unit_sphere(rng);
+            if (fabsf(sdir.x) < 1e-8 && fabsf(sdir.y) < 1e-8 && fabsf(sdir.z) < 1e-8) sdir = normal;
+            attenuation = base;
+        } else if (type == 1 /* METAL */) {  // material.h:133-140
+            float fuzz = m2.y < 1 ? m2.y : 1;
+            float3 reflected = reflect3(normalize(d), normal);
+            sdir = reflected + fuzz * random_in_unit_sphere(rng);
+            attenuation = base;
+            scattered = dot(sdir, normal) > 0;
+        } else {  // DIELECTRIC, material.h:149-179
+            const float ir = m2.z;
+            float3 outward_normal;
+            float3 reflected = reflect3(d, normal);
+            float ni_over_nt;
+            attenuation = f3(1.0f, 1.0f, 1.0f);
+            float3 refracted = f3(0.f, 0.f, 0.f);
+            float reflect_prob;
+            float cosine;
+            if (dot(d, normal) > 0.0f) {
+                outward_normal = -normal;
+                ni_over_nt = ir;
+                cosine = dot(d, normal) / length(d);
+                cosine = sqrtf(1.0f - ir * ir * (1 - cosine * cosine));
+            } else {
+                outward_normal = normal;
+                ni_over_nt = 1.0f / ir;
+                cosine = -dot(d, normal) / length(d);
+            }
+            if (refract3(d, outward_normal, ni_over_nt, refracted)) reflect_prob = schlick(cosine, ir);
+            else reflect_prob = 1.0f;
+            if (rng_uniform(rng) < reflect_prob) sdir = reflected;
+            else sdir = refracted;
+        }
+        if (!scattered) {
+            contrib = f3(0.f, 0.f, 0.f);
+            return false;
+        }
+        att = att * attenuation;
+        o = p;
+        d = sdir;
+        return true;
+    }
+    contrib = f3(0.f, 0.f, 0.f);
+    return false;
+}
+
+}  // namespace ptc

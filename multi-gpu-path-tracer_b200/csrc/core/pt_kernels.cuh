@@ -1,0 +1,220 @@
+// pt_kernels.cuh — the render kernels (sm_100a).
+//
+// pt_persistent_kernel replaces the reference's `render` kernel (src/DevicePathTracer.h:73-120:
+// one thread per pixel, spp loop, virtual-dispatch ray_color inlined, 103 registers + 672 B stack).
+// Organisation here: a persistent grid (SMs x resident CTAs) whose lanes each own one pixel's
+// XORWOW stream and run a per-lane wavefront
+//        GENERATE (camera ray / next sample / next pixel)  ->  TRAVERSE  ->  SHADE  -> (COMPACT)
+// in warp lock-step; a lane whose pixel has finished its spp refills itself from a global work
+// counter with one warp-aggregated atomic (the "compact" stage: idle lanes are replaced, live
+// ones keep their registers), so every lane carries a ray into every TRAVERSE stage until the
+// launch runs out of pixels.  Exact RNG-stream reproduction pins "one in-flight path per pixel,
+// samples sequential" (SURVEY §0.7), which is why the unit of refill is a pixel, not a ray.
+//
+// pt_direct_kernel is the plain parity slice (one thread per pixel, no refill), kept as the
+// A/B baseline for the scheduling choice.
+#pragma once
+
+#include "pt_device.cuh"
+
+namespace ptc {
+
+constexpr int kBlockThreads = 128;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// work item -> pixel.  Items enumerate 8x4 pixel blocks of each tile (32 consecutive items = one
+// block = one warp's initial fetch), so warps start on spatially coherent rays.
+__device__ __forceinline__ bool item_to_pixel(const TileList &tl, uint32_t item, int &x, int &y) {
+    int t = 0;
+    // tiles are few (<= kMaxInlineTiles): linear scan over the prefix sums
+    while (t + 1 < tl.n && item >= tl.first_item[t + 1]) t++;
+    uint32_t local = item - tl.first_item[t];
+    uint32_t blk = local >> 5, within = local & 31u;
+    uint32_t blocks_per_row = ((uint32_t)tl.w[t] + 7u) >> 3;
+    uint32_t by = blk / blocks_per_row, bx = blk - by * blocks_per_row;
+    int lx = (int)(bx * 8u + (within & 7u));
+    int ly = (int)(by * 4u + (within >> 3));
+    x = tl.ox[t] + lx;
+    y = tl.oy[t] + ly;
+    return lx < tl.w[t] && ly < tl.h[t];
+}
+
+template <bool SPHERES, bool RTOW, bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads) pt_persistent_kernel(const __grid_constant__ RenderParams p) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t total_items = p.tiles.first_item[p.tiles.n];
+
+    // per-lane pixel state
+    bool retired = false;     // no more work for this lane
+    bool have_pixel = false;  // owns a pixel whose samples are not finished
+    bool have_path = false;   // carries a live ray
+    int px = 0, py = 0, pixel_index = 0;
+    uint32_t samples_done = 0, bounce = 0;
+    Rng rng;
+    rng_init(rng, 0);
+    float3 col = f3(0.f, 0.f, 0.f), att = f3(1.f, 1.f, 1.f), ro = f3(0.f, 0.f, 0.f), rd = f3(0.f, 0.f, 1.f);
+    uint32_t n_rays = 0, n_box = 0, n_tri = 0, n_light = 0;
+    unsigned long long acc_box = 0, acc_tri = 0, acc_light = 0;
+
+    for (;;) {
+        // ---------------- GENERATE / COMPACT ----------------
+        if (!have_path && have_pixel && samples_done == p.spp) {
+            store_pixel(p, pixel_index, col);
+            have_pixel = false;
+        }
+        const bool need = !retired && !have_pixel;
+        const unsigned need_mask = __ballot_sync(kFullMask, need);
+        if (need_mask) {
+            const int leader = __ffs((int)need_mask) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(p.work_counter, (uint32_t)__popc(need_mask));
+            base = __shfl_sync(kFullMask, base, leader);
+            if (need) {
+                const uint32_t item = base + (uint32_t)__popc(need_mask & ((1u << lane) - 1u));
+                if (item >= total_items) {
+                    retired = true;
+                } else if (item_to_pixel(p.tiles, item, px, py)) {
+                    // DevicePathTracer.h:79: framebuffer row 0 is the top image row; :54: seed = 1984 + pixel_index
+                    pixel_index = ((int)p.height - py - 1) * (int)p.width + px;
+                    rng_init(rng, (unsigned long long)(long long)(1984 + pixel_index));
+                    col = f3(0.f, 0.f, 0.f);
+                    samples_done = 0;
+                    have_pixel = true;
+                }
+            }
+        }
+        if (__all_sync(kFullMask, retired)) break;
+
+        if (!have_path && have_pixel && samples_done < p.spp) {
+            // DevicePathTracer.h:84-87
+            float u = float(px + rng_uniform(rng)) / float(p.width);
+            float v = float(py + rng_uniform(rng)) / float(p.height);
+            camera_ray(p.cam, u, v, ro, rd);
+            att = f3(1.0f, 1.0f, 1.0f);
+            bounce = 0;
+            have_path = true;
+            if (p.depth == 0) {  // camera.h:52,82: the loop body never runs
+                have_path = false;
+                samples_done++;
+            }
+        }
+
+        // ---------------- TRAVERSE ----------------
+        Hit h;
+        h.prim = -1;
+        h.t = FLT_MAX;
+        h.u = h.v = 0.f;
+        if (have_path) {
+            h = closest_hit<SPHERES, COUNT>(p.scene, ro, rd, 0.001f, n_box, n_tri);
+            n_rays++;
+        }
+
+        // ---------------- SHADE ----------------
+        if (have_path) {
+            float3 contrib;
+            bool cont = shade<SPHERES, RTOW, COUNT>(p.scene, h, ro, rd, att, rng, contrib, n_light);
+            bounce++;
+            if (!cont) {
+                col = col + contrib;  // DevicePathTracer.h:87
+                have_path = false;
+                samples_done++;
+            } else if (bounce >= p.depth) {
+                // camera.h:82: recursion exhausted -> (0,0,0); col += 0 keeps NaN/inf behaviour identical
+                col = col + f3(0.0f, 0.0f, 0.0f);
+                have_path = false;
+                samples_done++;
+            }
+        }
+        if (COUNT) {
+            acc_box += n_box; acc_tri += n_tri; acc_light += n_light;
+            n_box = n_tri = n_light = 0;
+        }
+    }
+
+    // counters: one atomic per warp
+    unsigned long long r = n_rays;
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(kFullMask, r, o);
+    if (lane == 0 && r) atomicAdd(&p.counters->rays, r);
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            acc_box += __shfl_down_sync(kFullMask, acc_box, o);
+            acc_tri += __shfl_down_sync(kFullMask, acc_tri, o);
+            acc_light += __shfl_down_sync(kFullMask, acc_light, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&p.counters->box_tests, acc_box);
+            atomicAdd(&p.counters->tri_tests, acc_tri);
+            atomicAdd(&p.counters->light_tests, acc_light);
+        }
+    }
+}
+
+// One thread per pixel of ONE tile (tiles.n == 1), 8x4 blocks per warp, no refill.
+template <bool SPHERES, bool RTOW, bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads) pt_direct_kernel(const __grid_constant__ RenderParams p) {
+    const uint32_t item = blockIdx.x * (uint32_t)blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t n_rays = 0, n_box = 0, n_tri = 0, n_light = 0;
+    int px, py;
+    if (item < p.tiles.first_item[p.tiles.n] && item_to_pixel(p.tiles, item, px, py)) {
+        const int pixel_index = ((int)p.height - py - 1) * (int)p.width + px;
+        Rng rng;
+        rng_init(rng, (unsigned long long)(long long)(1984 + pixel_index));
+        float3 col = f3(0.f, 0.f, 0.f);
+        for (uint32_t s = 0; s < p.spp; s++) {
+            float u = float(px + rng_uniform(rng)) / float(p.width);
+            float v = float(py + rng_uniform(rng)) / float(p.height);
+            float3 ro, rd;
+            camera_ray(p.cam, u, v, ro, rd);
+            float3 att = f3(1.0f, 1.0f, 1.0f);
+            float3 contrib = f3(0.0f, 0.0f, 0.0f);
+            for (uint32_t i = 0; i < p.depth; i++) {
+                Hit h = closest_hit<SPHERES, COUNT>(p.scene, ro, rd, 0.001f, n_box, n_tri);
+                n_rays++;
+                if (!shade<SPHERES, RTOW, COUNT>(p.scene, h, ro, rd, att, rng, contrib, n_light)) break;
+                contrib = f3(0.0f, 0.0f, 0.0f);
+            }
+            col = col + contrib;
+        }
+        store_pixel(p, pixel_index, col);
+    }
+    unsigned long long r = n_rays, b = n_box, t = n_tri, l = n_light;
+    for (int o = 16; o > 0; o >>= 1) {
+        r += __shfl_down_sync(kFullMask, r, o);
+        if (COUNT) {
+            b += __shfl_down_sync(kFullMask, b, o);
+            t += __shfl_down_sync(kFullMask, t, o);
+            l += __shfl_down_sync(kFullMask, l, o);
+        }
+    }
+    if (lane == 0) {
+        if (r) atomicAdd(&p.counters->rays, r);
+        if (COUNT) {
+            atomicAdd(&p.counters->box_tests, b);
+            atomicAdd(&p.counters->tri_tests, t);
+            atomicAdd(&p.counters->light_tests, l);
+        }
+    }
+}
+
+// camera.h:21-36 evaluated with the device's own tanf / rsqrtf so the numbers are the ones the
+// reference's kernels compute (there: by every thread for every sample, into a shared object).
+__global__ void pt_camera_kernel(float3 lookFrom, float3 front, float vfov, float hfov, CamParams *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float3 vup = f3(0.0f, 1.0f, 0.0f);
+    float3 lookAt = lookFrom + front;
+    float theta_v = vfov * PT_M_PI / 180;
+    float half_height = tanf(theta_v / 2);
+    float theta_h = hfov * PT_M_PI / 180;
+    float half_width = tanf(theta_h / 2);
+    float3 origin = lookFrom;
+    float3 w = normalize(lookFrom - lookAt);
+    float3 u = normalize(cross(vup, w));
+    float3 v = cross(w, u);
+    out->origin = origin;
+    out->lower_left_corner = origin - half_width * u - half_height * v - w;
+    out->horizontal = 2 * half_width * u;
+    out->vertical = 2 * half_height * v;
+}
+
+}  // namespace ptc

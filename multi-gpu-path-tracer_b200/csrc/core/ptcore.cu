@@ -1,0 +1,591 @@
+// ptcore.cu — C ABI implementation (include/ptcore.h): scene compile + upload, camera,
+// framebuffer binding, kernel launches, statistics.  Host code here is the B200-native
+// counterpart of DevicePathTracer's methods (reference src/DevicePathTracer.h:167-392).
+#include "../../../include/ptcore.h"
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "bvh_builder.h"
+#include "pt_kernels.cuh"
+
+using namespace ptc;
+
+namespace {
+
+constexpr int kCounterRing = 1024;
+
+thread_local std::string g_create_error;
+
+struct SceneBlob {
+    std::vector<uint8_t> host;  // staged copy (pinned separately below)
+    uint8_t *pinned = nullptr;
+    uint8_t *dev = nullptr;
+    size_t bytes = 0;
+    size_t off_nodes = 0, off_prims = 0, off_shade = 0, off_mats = 0, off_texdesc = 0, off_texels = 0, off_lights = 0;
+    int32_t n_prims = 0, n_lights = 0, n_nodes = 0;
+    bool has_spheres = false, has_rtow = false;
+};
+
+}  // namespace
+
+struct ptcore {
+    int device = 0;
+    int sm_count = 0;
+    std::string error;
+    std::mutex mu;
+
+    SceneBlob blob;
+    bool have_scene = false;
+    DevScene dscene{};
+
+    CamParams cam{};
+    bool have_cam = false;
+    CamParams *d_cam = nullptr;
+
+    uint32_t spp = 10, depth = 3;  // RendererConfig defaults, src/RendererConfig.h:22-23
+    uint32_t bx = 8, by = 8;
+
+    uint8_t *fb_rgb = nullptr, *fb_yuv = nullptr;
+    uint32_t fb_w = 0, fb_h = 0;
+    uint8_t *own_rgb = nullptr, *own_yuv = nullptr;  // internal framebuffer of ptcore_render_frame_host
+    uint32_t own_w = 0, own_h = 0;
+
+    uint32_t *d_work = nullptr;
+    std::atomic<uint64_t> launch_seq{0};
+    DevCounters *d_counters = nullptr;
+    std::atomic<uint64_t> samples{0}, launches{0};
+
+    int kernel = PT_KERNEL_PERSISTENT;
+    bool count_tests = false;
+    int leaf_max = 4;
+    int blocks_per_sm = 0;
+    int slice_spp = 0;
+
+    PtStats build_stats{};
+};
+
+namespace {
+
+int fail(ptcore *h, int code, const std::string &msg) {
+    if (h) h->error = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define PT_CUDA(h, call)                                                                                        \
+    do {                                                                                                        \
+        cudaError_t e_ = (call);                                                                                \
+        if (e_ != cudaSuccess) {                                                                                \
+            return fail((h), (int)e_, std::string(#call) + ": " + cudaGetErrorName(e_) + " (" + cudaGetErrorString(e_) + ")"); \
+        }                                                                                                       \
+    } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline float as_float(int32_t i) {
+    float f;
+    memcpy(&f, &i, 4);
+    return f;
+}
+
+// triangle.h:28 — evaluated on the host by the reference as well (the triangle constructor is host code)
+float triangle_area_host(const float *p) {
+    float e1[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]};
+    float e2[3] = {p[6] - p[0], p[7] - p[1], p[8] - p[2]};
+    float cx = e1[1] * e2[2] - e1[2] * e2[1];
+    float cy = e1[2] * e2[0] - e1[0] * e2[2];
+    float cz = e1[0] * e2[1] - e1[1] * e2[0];
+    float d = cx * cx + cy * cy + cz * cz;
+    return sqrtf(d) * 0.5f;
+}
+
+template <bool S, bool R, bool C>
+cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaStream_t stream) {
+    const uint32_t total = rp.tiles.first_item[rp.tiles.n];
+    if (total == 0) return cudaSuccess;
+    if (direct) {
+        dim3 grid((total + kBlockThreads - 1) / kBlockThreads);
+        pt_direct_kernel<S, R, C><<<grid, kBlockThreads, 0, stream>>>(rp);
+    } else {
+        int occ = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_persistent_kernel<S, R, C>, kBlockThreads, 0);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+        if (h->blocks_per_sm > 0) occ = std::min(occ, h->blocks_per_sm);
+        uint32_t grid = (uint32_t)h->sm_count * (uint32_t)occ;
+        uint32_t needed = (total + kBlockThreads - 1) / kBlockThreads;
+        if (grid > needed) grid = needed;
+        pt_persistent_kernel<S, R, C><<<grid, kBlockThreads, 0, stream>>>(rp);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch(ptcore *h, const RenderParams &rp, cudaStream_t stream) {
+    const bool direct = h->kernel == PT_KERNEL_DIRECT;
+    const bool S = h->blob.has_spheres, R = h->blob.has_rtow, C = h->count_tests;
+    if (!S && !R && !C) return launch_variant<false, false, false>(h, rp, direct, stream);
+    if (!S && !R && C) return launch_variant<false, false, true>(h, rp, direct, stream);
+    if (!S && R && !C) return launch_variant<false, true, false>(h, rp, direct, stream);
+    if (!S && R && C) return launch_variant<false, true, true>(h, rp, direct, stream);
+    if (S && !R && !C) return launch_variant<true, false, false>(h, rp, direct, stream);
+    if (S && !R && C) return launch_variant<true, false, true>(h, rp, direct, stream);
+    if (S && R && !C) return launch_variant<true, true, false>(h, rp, direct, stream);
+    return launch_variant<true, true, true>(h, rp, direct, stream);
+}
+
+void fill_dev_scene(ptcore *h) {
+    SceneBlob &b = h->blob;
+    DevScene &d = h->dscene;
+    d.nodes = reinterpret_cast<const float4 *>(b.dev + b.off_nodes);
+    d.prims = reinterpret_cast<const float4 *>(b.dev + b.off_prims);
+    d.shade = reinterpret_cast<const float4 *>(b.dev + b.off_shade);
+    d.mats = reinterpret_cast<const float4 *>(b.dev + b.off_mats);
+    d.texs = reinterpret_cast<const TexDesc *>(b.dev + b.off_texdesc);
+    d.texels = reinterpret_cast<const float4 *>(b.dev + b.off_texels);
+    d.lights = reinterpret_cast<const float4 *>(b.dev + b.off_lights);
+    d.n_lights = b.n_lights;
+    d.n_prims = b.n_prims;
+    d.light_pick_scale = (b.n_lights - 1) + 0.999999;  // hitable_list.h:24
+    d.light_weight = b.n_lights > 0 ? 1.0f / b.n_lights : 0.f;
+    d.pad = 0;
+}
+
+int render_tiles(ptcore *h, const PtTile *tiles, int32_t n_tiles, cudaStream_t stream) {
+    if (!h->have_scene) return fail(h, PT_ERR_NO_SCENE, "no scene uploaded");
+    if (!h->fb_rgb) return fail(h, PT_ERR_NO_FRAMEBUFFER, "no framebuffer bound");
+    if (!h->have_cam) return fail(h, PT_ERR_INVALID_ARGUMENT, "no camera set");
+    PT_CUDA(h, cudaSetDevice(h->device));
+    int32_t done = 0;
+    while (done < n_tiles) {
+        RenderParams rp;
+        rp.scene = h->dscene;
+        rp.cam = h->cam;
+        rp.width = h->fb_w;
+        rp.height = h->fb_h;
+        rp.spp = h->spp;
+        rp.depth = h->depth;
+        rp.fb_rgb = h->fb_rgb;
+        rp.fb_yuv = h->fb_yuv;
+        rp.counters = h->d_counters;
+        TileList &tl = rp.tiles;
+        tl.n = 0;
+        tl.first_item[0] = 0;
+        uint64_t pixels = 0;
+        const bool direct = h->kernel == PT_KERNEL_DIRECT;
+        while (done < n_tiles && tl.n < (direct ? 1 : kMaxInlineTiles)) {
+            PtTile t = tiles[done];
+            // clip to the framebuffer (the reference over-provisions its grid and relies on the i/j guard, :75)
+            int32_t x0 = std::max(t.offset_x, 0), y0 = std::max(t.offset_y, 0);
+            int32_t x1 = std::min<int64_t>((int64_t)t.offset_x + t.width, h->fb_w), y1 = std::min<int64_t>((int64_t)t.offset_y + t.height, h->fb_h);
+            done++;
+            if (t.width <= 0 || t.height <= 0 || x1 <= x0 || y1 <= y0) continue;  // renderTaskAsync :195: width == 0 is a no-op
+            uint64_t items = 32ull * (uint64_t)((x1 - x0 + 7) / 8) * (uint64_t)((y1 - y0 + 3) / 4);
+            if ((uint64_t)tl.first_item[tl.n] + items > 0xfffffff0ull) { done--; break; }
+            tl.ox[tl.n] = x0; tl.oy[tl.n] = y0; tl.w[tl.n] = x1 - x0; tl.h[tl.n] = y1 - y0;
+            tl.first_item[tl.n + 1] = tl.first_item[tl.n] + (uint32_t)items;
+            pixels += (uint64_t)(x1 - x0) * (uint64_t)(y1 - y0);
+            tl.n++;
+        }
+        if (tl.n == 0) continue;
+        uint64_t seq = h->launch_seq.fetch_add(1);
+        rp.work_counter = h->d_work + (seq % kCounterRing);
+        if (!direct) PT_CUDA(h, cudaMemsetAsync(rp.work_counter, 0, sizeof(uint32_t), stream));
+        PT_CUDA(h, launch(h, rp, stream));
+        h->samples.fetch_add(pixels * h->spp);
+        h->launches.fetch_add(1);
+    }
+    return PT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ptcore_abi_version(void) { return PTCORE_ABI_VERSION; }
+
+const char *ptcore_last_error(const ptcore_t *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int ptcore_create(int device, ptcore_t **out) {
+    if (!out) return fail(nullptr, PT_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(nullptr, (int)e, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e) + " — libptcore needs a CUDA device; there is no CPU fallback");
+    if (device < 0 || device >= n) return fail(nullptr, PT_ERR_INVALID_ARGUMENT, "device index out of range");
+    ptcore *h = new ptcore();
+    h->device = device;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_work, sizeof(uint32_t) * kCounterRing);
+    if (e == cudaSuccess) e = cudaMemset(h->d_work, 0, sizeof(uint32_t) * kCounterRing);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_counters, sizeof(DevCounters));
+    if (e == cudaSuccess) e = cudaMemset(h->d_counters, 0, sizeof(DevCounters));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_cam, sizeof(CamParams));
+    if (e != cudaSuccess) {
+        int code = fail(nullptr, (int)e, std::string("ptcore_create: ") + cudaGetErrorString(e));
+        delete h;
+        return code;
+    }
+    *out = h;
+    return PT_OK;
+}
+
+int ptcore_destroy(ptcore_t *h) {
+    if (!h) return PT_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->d_work);
+    cudaFree(h->d_counters);
+    cudaFree(h->d_cam);
+    cudaFree(h->blob.dev);
+    if (h->blob.pinned) cudaFreeHost(h->blob.pinned);
+    cudaFree(h->own_rgb);
+    cudaFree(h->own_yuv);
+    delete h;
+    return PT_OK;
+}
+
+int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
+    if (!h || !sc) return fail(h, PT_ERR_INVALID_ARGUMENT, "null argument");
+    if (sc->n_tris < 0 || sc->n_spheres < 0 || sc->n_mats <= 0 || sc->n_tex < 0) return fail(h, PT_ERR_INVALID_ARGUMENT, "bad scene counts (at least one material is required)");
+    if ((sc->n_tris && (!sc->tri_pos || !sc->tri_mat)) || (sc->n_spheres && (!sc->sph || !sc->sph_mat)) || !sc->mats || (sc->n_tex && !sc->tex))
+        return fail(h, PT_ERR_INVALID_ARGUMENT, "scene arrays missing");
+    const int64_t n_prims = (int64_t)sc->n_tris + sc->n_spheres;
+    if (n_prims >= (1 << 28)) return fail(h, PT_ERR_UNSUPPORTED, "too many primitives for the leaf reference encoding");
+    for (int32_t i = 0; i < sc->n_tris; i++)
+        if (sc->tri_mat[i] < 0 || sc->tri_mat[i] >= sc->n_mats) return fail(h, PT_ERR_INVALID_ARGUMENT, "triangle material index out of range");
+    for (int32_t i = 0; i < sc->n_spheres; i++)
+        if (sc->sph_mat[i] < 0 || sc->sph_mat[i] >= sc->n_mats) return fail(h, PT_ERR_INVALID_ARGUMENT, "sphere material index out of range");
+    for (int32_t i = 0; i < sc->n_mats; i++) {
+        const PtMaterial &m = sc->mats[i];
+        if (m.type < 0 || m.type > PT_MAT_UNIVERSAL) return fail(h, PT_ERR_INVALID_ARGUMENT, "unknown material type");
+        if (m.base_tex >= sc->n_tex || m.emis_tex >= sc->n_tex) return fail(h, PT_ERR_INVALID_ARGUMENT, "material texture index out of range");
+    }
+    PT_CUDA(h, cudaSetDevice(h->device));
+    auto t0 = std::chrono::high_resolution_clock::now();
+
+    // ---- bounds (padded: the slab test must never cull a hit the primitive test accepts) ----
+    std::vector<PrimBounds> pb((size_t)n_prims);
+    for (int32_t i = 0; i < sc->n_tris; i++) {
+        const float *p = sc->tri_pos + (size_t)i * 9;
+        for (int k = 0; k < 3; k++) {
+            pb[(size_t)i].lo[k] = std::min(p[k], std::min(p[3 + k], p[6 + k]));
+            pb[(size_t)i].hi[k] = std::max(p[k], std::max(p[3 + k], p[6 + k]));
+        }
+    }
+    for (int32_t i = 0; i < sc->n_spheres; i++) {
+        const float *s = sc->sph + (size_t)i * 4;
+        float r = std::fabs(s[3]);
+        for (int k = 0; k < 3; k++) {
+            pb[(size_t)sc->n_tris + (size_t)i].lo[k] = s[k] - r;
+            pb[(size_t)sc->n_tris + (size_t)i].hi[k] = s[k] + r;
+        }
+    }
+    for (auto &b : pb)
+        for (int k = 0; k < 3; k++) {
+            float m = std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
+            float e = m * 1e-5f + 1e-6f;
+            b.lo[k] -= e;
+            b.hi[k] += e;
+        }
+
+    BvhBuildOptions opt;
+    opt.leaf_max = h->leaf_max;
+    BvhBuildResult bvh = build_bvh(pb, opt);
+
+    // ---- lights: DevicePathTracer.h:302-307 (emissiveFactor channel > 0.0001, scene order) ----
+    std::vector<int32_t> lights;
+    for (int32_t i = 0; i < sc->n_tris; i++) {
+        const PtMaterial &m = sc->mats[sc->tri_mat[i]];
+        if (m.type == PT_MAT_UNIVERSAL && (m.emis[0] > 0.0001 || m.emis[1] > 0.0001 || m.emis[2] > 0.0001)) lights.push_back(i);
+    }
+
+    // ---- blob layout ----
+    SceneBlob nb;
+    nb.n_prims = (int32_t)n_prims;
+    nb.n_lights = (int32_t)lights.size();
+    nb.n_nodes = (int32_t)bvh.nodes.size();
+    size_t texels = 0;
+    for (int32_t i = 0; i < sc->n_tex; i++) {
+        if (sc->tex[i].width < 0 || sc->tex[i].height < 0) return fail(h, PT_ERR_INVALID_ARGUMENT, "negative texture size");
+        texels += (size_t)sc->tex[i].width * (size_t)sc->tex[i].height;
+    }
+    if (texels >= 0xffffffffull) return fail(h, PT_ERR_UNSUPPORTED, "textures too large");
+    size_t off = 0;
+    nb.off_nodes = off; off = align_up(off + bvh.nodes.size() * sizeof(FlatNode), 256);
+    nb.off_prims = off; off = align_up(off + std::max<size_t>(1, (size_t)n_prims) * 48, 256);
+    nb.off_shade = off; off = align_up(off + std::max<size_t>(1, (size_t)n_prims) * 32, 256);
+    nb.off_mats = off; off = align_up(off + (size_t)sc->n_mats * 48, 256);
+    nb.off_texdesc = off; off = align_up(off + std::max<size_t>(1, (size_t)sc->n_tex) * sizeof(TexDesc), 256);
+    nb.off_texels = off; off = align_up(off + std::max<size_t>(1, texels) * 16, 256);
+    nb.off_lights = off; off = align_up(off + std::max<size_t>(1, lights.size()) * 48, 256);
+    nb.bytes = off;
+    nb.host.assign(nb.bytes, 0);
+
+    memcpy(nb.host.data() + nb.off_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(FlatNode));
+    float *prims = reinterpret_cast<float *>(nb.host.data() + nb.off_prims);
+    float *shade = reinterpret_cast<float *>(nb.host.data() + nb.off_shade);
+    for (int64_t k = 0; k < n_prims; k++) {
+        int32_t id = bvh.prim_order[(size_t)k];
+        float *q = prims + k * 12;
+        float *s = shade + k * 8;
+        if (id < sc->n_tris) {
+            const float *p = sc->tri_pos + (size_t)id * 9;
+            q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
+            q[3] = p[3] - p[0]; q[4] = p[4] - p[1]; q[5] = p[5] - p[2];  // e1 = v1 - v0, triangle.h:67
+            q[6] = p[6] - p[0]; q[7] = p[7] - p[1]; q[8] = p[8] - p[2];  // e2 = v2 - v0, triangle.h:68
+            q[9] = 0.f; q[10] = as_float(0); q[11] = 0.f;
+            if (sc->tri_uv) memcpy(s, sc->tri_uv + (size_t)id * 6, 6 * sizeof(float));
+            s[6] = as_float(sc->tri_mat[id]);
+        } else {
+            const int32_t si = id - sc->n_tris;
+            const float *sp = sc->sph + (size_t)si * 4;
+            q[0] = sp[0]; q[1] = sp[1]; q[2] = sp[2]; q[3] = sp[3];
+            q[10] = as_float(1);
+            s[6] = as_float(sc->sph_mat[si]);
+            nb.has_spheres = true;
+        }
+        s[7] = as_float(id);
+    }
+    float *mats = reinterpret_cast<float *>(nb.host.data() + nb.off_mats);
+    for (int32_t i = 0; i < sc->n_mats; i++) {
+        const PtMaterial &m = sc->mats[i];
+        float *q = mats + (size_t)i * 12;
+        q[0] = as_float(m.type); q[1] = m.base[0]; q[2] = m.base[1]; q[3] = m.base[2];
+        q[4] = m.emis[0]; q[5] = m.emis[1]; q[6] = m.emis[2]; q[7] = as_float(m.base_tex < 0 ? -1 : m.base_tex);
+        q[8] = as_float(m.emis_tex < 0 ? -1 : m.emis_tex); q[9] = m.fuzz; q[10] = m.ior; q[11] = 0.f;
+        if (m.type != PT_MAT_UNIVERSAL) nb.has_rtow = true;
+    }
+    TexDesc *td = reinterpret_cast<TexDesc *>(nb.host.data() + nb.off_texdesc);
+    float *tx = reinterpret_cast<float *>(nb.host.data() + nb.off_texels);
+    size_t texel_off = 0;
+    for (int32_t i = 0; i < sc->n_tex; i++) {
+        td[i].width = sc->tex[i].width;
+        td[i].height = sc->tex[i].rgb ? sc->tex[i].height : 0;
+        td[i].offset = (uint32_t)texel_off;
+        td[i].pad = 0;
+        size_t n = (size_t)sc->tex[i].width * (size_t)sc->tex[i].height;
+        if (sc->tex[i].rgb) {
+            const double color_scale = 1.0 / 255.0;  // Texture.h:45-46: the scale is a double, the product is rounded to float once
+            for (size_t k = 0; k < n; k++) {
+                float *o = tx + (texel_off + k) * 4;
+                o[0] = (float)(color_scale * sc->tex[i].rgb[k * 3 + 0]);
+                o[1] = (float)(color_scale * sc->tex[i].rgb[k * 3 + 1]);
+                o[2] = (float)(color_scale * sc->tex[i].rgb[k * 3 + 2]);
+                o[3] = 0.f;
+            }
+        }
+        texel_off += n;
+    }
+    float *lt = reinterpret_cast<float *>(nb.host.data() + nb.off_lights);
+    for (size_t i = 0; i < lights.size(); i++) {
+        const float *p = sc->tri_pos + (size_t)lights[i] * 9;
+        float *q = lt + i * 12;
+        q[0] = p[0]; q[1] = p[1]; q[2] = p[2]; q[3] = triangle_area_host(p);
+        q[4] = p[3]; q[5] = p[4]; q[6] = p[5]; q[7] = 0.f;
+        q[8] = p[6]; q[9] = p[7]; q[10] = p[8]; q[11] = 0.f;
+    }
+    auto t1 = std::chrono::high_resolution_clock::now();
+
+    // ---- one bulk upload ----
+    PT_CUDA(h, cudaDeviceSynchronize());
+    uint8_t *dev = nullptr, *pinned = nullptr;
+    PT_CUDA(h, cudaMalloc(&dev, nb.bytes));
+    cudaError_t e = cudaMallocHost(&pinned, nb.bytes);
+    if (e != cudaSuccess) { cudaFree(dev); return fail(h, (int)e, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
+    memcpy(pinned, nb.host.data(), nb.bytes);
+    e = cudaMemcpy(dev, pinned, nb.bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(dev); cudaFreeHost(pinned); return fail(h, (int)e, std::string("scene upload: ") + cudaGetErrorString(e)); }
+    cudaFree(h->blob.dev);
+    if (h->blob.pinned) cudaFreeHost(h->blob.pinned);
+    nb.dev = dev;
+    nb.pinned = pinned;
+    nb.host.clear();
+    nb.host.shrink_to_fit();
+    h->blob = std::move(nb);
+    fill_dev_scene(h);
+    h->have_scene = true;
+
+    h->build_stats.bvh_nodes = (uint32_t)bvh.nodes.size();
+    h->build_stats.bvh_leaves = bvh.n_leaves;
+    h->build_stats.bvh_depth = bvh.depth;
+    h->build_stats.n_lights = (uint32_t)lights.size();
+    h->build_stats.bvh_build_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    h->build_stats.sah_cost = bvh.sah_cost;
+    h->build_stats.scene_bytes = h->blob.bytes;
+    return PT_OK;
+}
+
+int ptcore_reupload_scene(ptcore_t *h, void *stream, uint64_t *bytes_copied) {
+    if (!h) return PT_ERR_INVALID_ARGUMENT;
+    if (!h->have_scene) return fail(h, PT_ERR_NO_SCENE, "no scene uploaded");
+    PT_CUDA(h, cudaSetDevice(h->device));
+    PT_CUDA(h, cudaMemcpyAsync(h->blob.dev, h->blob.pinned, h->blob.bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    if (bytes_copied) *bytes_copied = h->blob.bytes;
+    return PT_OK;
+}
+
+int ptcore_set_camera(ptcore_t *h, const PtCamera *cam) {
+    if (!h || !cam) return fail(h, PT_ERR_INVALID_ARGUMENT, "null argument");
+    PT_CUDA(h, cudaSetDevice(h->device));
+    pt_camera_kernel<<<1, 1>>>(make_float3(cam->look_from[0], cam->look_from[1], cam->look_from[2]), make_float3(cam->front[0], cam->front[1], cam->front[2]),
+                               cam->vfov, cam->hfov, h->d_cam);
+    PT_CUDA(h, cudaGetLastError());
+    PT_CUDA(h, cudaMemcpy(&h->cam, h->d_cam, sizeof(CamParams), cudaMemcpyDeviceToHost));
+    h->have_cam = true;
+    return PT_OK;
+}
+
+int ptcore_set_params(ptcore_t *h, uint32_t spp, uint32_t depth) {
+    if (!h) return PT_ERR_INVALID_ARGUMENT;
+    if (spp == 0) return fail(h, PT_ERR_INVALID_ARGUMENT, "samples_per_pixel must be >= 1");
+    h->spp = spp;
+    h->depth = depth;
+    return PT_OK;
+}
+
+int ptcore_set_thread_block_size(ptcore_t *h, uint32_t bx, uint32_t by) {
+    if (!h) return PT_ERR_INVALID_ARGUMENT;
+    if (bx == 0 || by == 0) return fail(h, PT_ERR_INVALID_ARGUMENT, "thread block size must be non-zero");
+    h->bx = bx;
+    h->by = by;
+    return PT_OK;
+}
+
+int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
+    if (!h) return PT_ERR_INVALID_ARGUMENT;
+    switch (key) {
+        case PT_OPT_KERNEL:
+            if (value != PT_KERNEL_PERSISTENT && value != PT_KERNEL_DIRECT) return fail(h, PT_ERR_INVALID_ARGUMENT, "unknown kernel");
+            h->kernel = (int)value;
+            return PT_OK;
+        case PT_OPT_COUNT_TESTS: h->count_tests = value != 0; return PT_OK;
+        case PT_OPT_BVH_LEAF_MAX:
+            if (value < 1 || value > kMaxLeafPrims) return fail(h, PT_ERR_INVALID_ARGUMENT, "leaf_max must be in [1, 8]");
+            h->leaf_max = (int)value;
+            return PT_OK;
+        case PT_OPT_BLOCKS_PER_SM:
+            if (value < 0 || value > 32) return fail(h, PT_ERR_INVALID_ARGUMENT, "blocks_per_sm must be in [0, 32]");
+            h->blocks_per_sm = (int)value;
+            return PT_OK;
+        case PT_OPT_SLICE_SPP:
+            if (value != 0) return fail(h, PT_ERR_UNSUPPORTED, "sample slicing is not implemented yet");
+            h->slice_spp = 0;
+            return PT_OK;
+        default: return fail(h, PT_ERR_UNSUPPORTED, "unknown option key");
+    }
+}
+
+int ptcore_bind_framebuffer(ptcore_t *h, uint8_t *rgb, uint8_t *yuv, uint32_t width, uint32_t height) {
+    if (!h) return PT_ERR_INVALID_ARGUMENT;
+    if (!rgb || width == 0 || height == 0) return fail(h, PT_ERR_INVALID_ARGUMENT, "framebuffer needs an RGB pointer and non-zero size");
+    if ((uint64_t)width * height > 0x7fffffffull / 3) return fail(h, PT_ERR_UNSUPPORTED, "framebuffer too large");
+    h->fb_rgb = rgb;
+    h->fb_yuv = yuv;
+    h->fb_w = width;
+    h->fb_h = height;
+    return PT_OK;
+}
+
+int ptcore_render_tile_async(ptcore_t *h, int32_t ox, int32_t oy, int32_t w, int32_t hgt, void *stream) {
+    if (!h) return PT_ERR_INVALID_ARGUMENT;
+    PtTile t{w, hgt, ox, oy};
+    return render_tiles(h, &t, 1, (cudaStream_t)stream);
+}
+
+int ptcore_render_tiles_async(ptcore_t *h, const PtTile *tiles, int32_t n, void *stream) {
+    if (!h || (n > 0 && !tiles) || n < 0) return fail(h, PT_ERR_INVALID_ARGUMENT, "bad tile list");
+    return render_tiles(h, tiles, n, (cudaStream_t)stream);
+}
+
+int ptcore_sync(ptcore_t *h, void *stream) {
+    if (!h) return PT_ERR_INVALID_ARGUMENT;
+    PT_CUDA(h, cudaSetDevice(h->device));
+    PT_CUDA(h, cudaGetLastError());
+    PT_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+    return PT_OK;
+}
+
+int ptcore_wait(ptcore_t *h) {
+    if (!h) return PT_ERR_INVALID_ARGUMENT;
+    PT_CUDA(h, cudaSetDevice(h->device));
+    PT_CUDA(h, cudaGetLastError());
+    PT_CUDA(h, cudaDeviceSynchronize());
+    return PT_OK;
+}
+
+int ptcore_render_frame_host(ptcore_t *h, uint32_t width, uint32_t height, uint8_t *rgb_host, uint8_t *yuv_host) {
+    if (!h || !rgb_host || width == 0 || height == 0) return fail(h, PT_ERR_INVALID_ARGUMENT, "bad arguments");
+    PT_CUDA(h, cudaSetDevice(h->device));
+    const size_t px = (size_t)width * height;
+    if (h->own_w != width || h->own_h != height) {
+        cudaFree(h->own_rgb);
+        cudaFree(h->own_yuv);
+        h->own_rgb = h->own_yuv = nullptr;
+        h->own_w = h->own_h = 0;
+        PT_CUDA(h, cudaMalloc(&h->own_rgb, px * 3));
+        PT_CUDA(h, cudaMalloc(&h->own_yuv, px * 3 / 2 + 2));
+        h->own_w = width;
+        h->own_h = height;
+    }
+    uint8_t *srgb = h->fb_rgb, *syuv = h->fb_yuv;
+    uint32_t sw = h->fb_w, sh = h->fb_h;
+    h->fb_rgb = h->own_rgb;
+    h->fb_yuv = yuv_host ? h->own_yuv : nullptr;
+    h->fb_w = width;
+    h->fb_h = height;
+    PtTile t{(int32_t)width, (int32_t)height, 0, 0};
+    int rc = render_tiles(h, &t, 1, nullptr);
+    h->fb_rgb = srgb; h->fb_yuv = syuv; h->fb_w = sw; h->fb_h = sh;
+    if (rc != PT_OK) return rc;
+    PT_CUDA(h, cudaMemcpyAsync(rgb_host, h->own_rgb, px * 3, cudaMemcpyDeviceToHost, nullptr));
+    if (yuv_host) PT_CUDA(h, cudaMemcpyAsync(yuv_host, h->own_yuv, px * 3 / 2, cudaMemcpyDeviceToHost, nullptr));
+    PT_CUDA(h, cudaStreamSynchronize(nullptr));
+    return PT_OK;
+}
+
+int ptcore_get_stats(ptcore_t *h, PtStats *out) {
+    if (!h || !out) return fail(h, PT_ERR_INVALID_ARGUMENT, "null argument");
+    PT_CUDA(h, cudaSetDevice(h->device));
+    PT_CUDA(h, cudaDeviceSynchronize());
+    DevCounters c;
+    PT_CUDA(h, cudaMemcpy(&c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    *out = h->build_stats;
+    out->samples = h->samples.load();
+    out->rays = c.rays;
+    out->box_tests = c.box_tests;
+    out->tri_tests = c.tri_tests;
+    out->light_tests = c.light_tests;
+    out->launches = h->launches.load();
+    return PT_OK;
+}
+
+int ptcore_reset_stats(ptcore_t *h) {
+    if (!h) return PT_ERR_INVALID_ARGUMENT;
+    PT_CUDA(h, cudaSetDevice(h->device));
+    PT_CUDA(h, cudaDeviceSynchronize());
+    PT_CUDA(h, cudaMemset(h->d_counters, 0, sizeof(DevCounters)));
+    h->samples = 0;
+    h->launches = 0;
+    return PT_OK;
+}
+
+int pt_write_ppm(const char *path, const uint8_t *rgb, uint32_t width, uint32_t height) {
+    if (!path || !rgb) return PT_ERR_INVALID_ARGUMENT;
+    FILE *f = fopen(path, "wb");
+    if (!f) return PT_ERR_SYSTEM;
+    fprintf(f, "P6\n%u %u\n255\n", width, height);
+    size_t n = (size_t)width * height * 3;
+    size_t w = fwrite(rgb, 1, n, f);
+    fclose(f);
+    return w == n ? PT_OK : PT_ERR_SYSTEM;
+}
+
+}  // extern "C"
