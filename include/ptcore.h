@@ -163,6 +163,12 @@ int ptcore_render_frame_host(ptcore_t *h, uint32_t width, uint32_t height, uint8
 int ptcore_get_stats(ptcore_t *h, PtStats *out); /* synchronises the device */
 int ptcore_reset_stats(ptcore_t *h);
 
+/* ---- parity probe: walks ONE pixel (current spp/depth/camera/scene) with one device thread and records every
+ *      ray as 16 floats: sample, bounce, original primitive id (-1 = miss), t, bary u, bary v, origin xyz,
+ *      direction xyz, throughput xyz before shading, 0.  col receives the un-quantised pixel sum. ---- */
+int ptcore_debug_trace_pixel(ptcore_t *h, uint32_t width, uint32_t height, int32_t x, int32_t y, float *events, int32_t max_events,
+                             int32_t *n_events, float *col);
+
 /* ---- multi-GPU plumbing: a tile counter shared by the ranks of one node (POSIX shared memory).
  *      Replaces the per-frame static rectangles of RenderManager/TaskGenerator
  *      (src/RenderManager.h:42-59, src/Scheduling/TaskGenerator.h:58-80) with dynamic claims. ---- */

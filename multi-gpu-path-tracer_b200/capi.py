@@ -199,6 +199,7 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         "ptcore_render_frame_host": (C.c_int, [vp, u32, u32, vp, vp]),
         "ptcore_get_stats": (C.c_int, [vp, C.POINTER(PtStats)]),
         "ptcore_reset_stats": (C.c_int, [vp]),
+        "ptcore_debug_trace_pixel": (C.c_int, [vp, u32, u32, i32, i32, vp, i32, C.POINTER(i32), vp]),
         "pt_tileq_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
         "pt_tileq_claim": (i64, [vp, i64, i64]),
         "pt_tileq_reset": (C.c_int, [vp]),
@@ -338,6 +339,14 @@ class PathTracer:
             yuv = np.empty((width * height * 3 // 2,), np.uint8)
         self._ck(self.lib.ptcore_render_frame_host(self.h, width, height, rgb.ctypes.data, yuv.ctypes.data if want_yuv else None))
         return rgb, (yuv if want_yuv else None)
+
+    def trace_pixel(self, width: int, height: int, x: int, y: int, max_events: int = 4096):
+        """Parity probe: (events[n,16] float32, col[3]) for one pixel with the current scene/camera/params."""
+        ev = np.zeros((max_events, 16), np.float32)
+        col = np.zeros(3, np.float32)
+        n = C.c_int32()
+        self._ck(self.lib.ptcore_debug_trace_pixel(self.h, width, height, x, y, ev.ctypes.data, max_events, C.byref(n), col.ctypes.data))
+        return ev[: min(n.value, max_events)], col
 
     def stats(self) -> dict:
         st = PtStats()

@@ -197,6 +197,45 @@ __global__ void __launch_bounds__(kBlockThreads) pt_direct_kernel(const __grid_c
     }
 }
 
+// Debug/parity probe: one thread walks ONE pixel exactly like the render kernels do and records every ray
+// (16 floats per event: sample, bounce, original primitive id or -1, t, bary u, bary v, origin xyz, direction xyz,
+// throughput xyz before shading, 0).  Used by tests to find the first event where CUDA and the oracle part ways.
+template <bool SPHERES, bool RTOW>
+__global__ void pt_trace_kernel(const __grid_constant__ RenderParams p, int px, int py, float *events, int max_events, int *n_events, float *col_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int pixel_index = ((int)p.height - py - 1) * (int)p.width + px;
+    Rng rng;
+    rng_init(rng, (unsigned long long)(long long)(1984 + pixel_index));
+    float3 col = f3(0.f, 0.f, 0.f);
+    int n = 0;
+    uint32_t nb = 0, nt = 0, nl = 0;
+    for (uint32_t s = 0; s < p.spp; s++) {
+        float u = float(px + rng_uniform(rng)) / float(p.width);
+        float v = float(py + rng_uniform(rng)) / float(p.height);
+        float3 ro, rd;
+        camera_ray(p.cam, u, v, ro, rd);
+        float3 att = f3(1.0f, 1.0f, 1.0f);
+        float3 contrib = f3(0.0f, 0.0f, 0.0f);
+        for (uint32_t i = 0; i < p.depth; i++) {
+            Hit h = closest_hit<SPHERES, false>(p.scene, ro, rd, 0.001f, nb, nt);
+            if (n < max_events) {
+                float *e = events + (size_t)n * 16;
+                e[0] = (float)s; e[1] = (float)i;
+                e[2] = h.prim < 0 ? -1.f : (float)__float_as_int(__ldg(&p.scene.shade[h.prim * 2 + 1]).w);
+                e[3] = h.t; e[4] = h.u; e[5] = h.v;
+                e[6] = ro.x; e[7] = ro.y; e[8] = ro.z; e[9] = rd.x; e[10] = rd.y; e[11] = rd.z;
+                e[12] = att.x; e[13] = att.y; e[14] = att.z; e[15] = 0.f;
+            }
+            n++;
+            if (!shade<SPHERES, RTOW, false>(p.scene, h, ro, rd, att, rng, contrib, nl)) break;
+            contrib = f3(0.0f, 0.0f, 0.0f);
+        }
+        col = col + contrib;
+    }
+    *n_events = n;
+    col_out[0] = col.x; col_out[1] = col.y; col_out[2] = col.z;
+}
+
 // camera.h:21-36 evaluated with the device's own tanf / rsqrtf so the numbers are the ones the
 // reference's kernels compute (there: by every thread for every sample, into a shared object).
 __global__ void pt_camera_kernel(float3 lookFrom, float3 front, float vfov, float hfov, CamParams *out) {

@@ -577,6 +577,35 @@ int ptcore_reset_stats(ptcore_t *h) {
     return PT_OK;
 }
 
+int ptcore_debug_trace_pixel(ptcore_t *h, uint32_t width, uint32_t height, int32_t x, int32_t y, float *events, int32_t max_events, int32_t *n_events, float *col) {
+    if (!h || !events || !n_events || !col || max_events <= 0) return fail(h, PT_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (!h->have_scene) return fail(h, PT_ERR_NO_SCENE, "no scene uploaded");
+    if (!h->have_cam) return fail(h, PT_ERR_INVALID_ARGUMENT, "no camera set");
+    PT_CUDA(h, cudaSetDevice(h->device));
+    float *d_events = nullptr, *d_col = nullptr;
+    int *d_n = nullptr;
+    PT_CUDA(h, cudaMalloc(&d_events, sizeof(float) * 16 * (size_t)max_events));
+    PT_CUDA(h, cudaMalloc(&d_col, sizeof(float) * 3));
+    PT_CUDA(h, cudaMalloc(&d_n, sizeof(int)));
+    RenderParams rp{};
+    rp.scene = h->dscene;
+    rp.cam = h->cam;
+    rp.width = width; rp.height = height; rp.spp = h->spp; rp.depth = h->depth;
+    rp.counters = h->d_counters;
+    const bool S = h->blob.has_spheres, R = h->blob.has_rtow;
+    if (!S && !R) pt_trace_kernel<false, false><<<1, 1>>>(rp, x, y, d_events, max_events, d_n, d_col);
+    else if (!S && R) pt_trace_kernel<false, true><<<1, 1>>>(rp, x, y, d_events, max_events, d_n, d_col);
+    else if (S && !R) pt_trace_kernel<true, false><<<1, 1>>>(rp, x, y, d_events, max_events, d_n, d_col);
+    else pt_trace_kernel<true, true><<<1, 1>>>(rp, x, y, d_events, max_events, d_n, d_col);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(n_events, d_n, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(col, d_col, sizeof(float) * 3, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(events, d_events, sizeof(float) * 16 * (size_t)std::min(*n_events, max_events), cudaMemcpyDeviceToHost);
+    cudaFree(d_events); cudaFree(d_col); cudaFree(d_n);
+    if (e != cudaSuccess) return fail(h, (int)e, std::string("ptcore_debug_trace_pixel: ") + cudaGetErrorString(e));
+    return PT_OK;
+}
+
 int pt_write_ppm(const char *path, const uint8_t *rgb, uint32_t width, uint32_t height) {
     if (!path || !rgb) return PT_ERR_INVALID_ARGUMENT;
     FILE *f = fopen(path, "wb");

@@ -85,7 +85,7 @@ float pto_uniform(pto_rng *s) {
     return (float)x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
 }
 
-typedef struct { pto_rng *s; pto_stats *st; } rng_ctx;
+typedef struct { pto_rng *s; pto_stats *st; float *events; int max_events, n_events; float cur_sample; } rng_ctx;
 static inline float U(rng_ctx *c) {
     if (c->st) c->st->draws++;
     return pto_uniform(c->s);
@@ -102,7 +102,7 @@ static v3 random_cosine_direction(rng_ctx *c) {
     float y = sinf(phi) * 2 * sqrtf(r2);
     return V(x, y, z);
 }
-pto_vec3 pto_random_cosine_direction(pto_rng *s) { rng_ctx c = {s, NULL}; return random_cosine_direction(&c); }
+pto_vec3 pto_random_cosine_direction(pto_rng *s) { rng_ctx c = {s, NULL, NULL, 0, 0, 0.f}; return random_cosine_direction(&c); }
 
 static v3 random_in_unit_sphere(rng_ctx *c) {
     /* helper_math.h:1504-1518; draw order x,y,z (builder-defined, see header comment) */
@@ -113,7 +113,7 @@ static v3 random_in_unit_sphere(rng_ctx *c) {
     } while (vdot(p, p) >= 1.0f);
     return p;
 }
-pto_vec3 pto_random_in_unit_sphere(pto_rng *s) { rng_ctx c = {s, NULL}; return random_in_unit_sphere(&c); }
+pto_vec3 pto_random_in_unit_sphere(pto_rng *s) { rng_ctx c = {s, NULL, NULL, 0, 0, 0.f}; return random_in_unit_sphere(&c); }
 
 void pto_onb(pto_vec3 n, pto_vec3 axis[3]) {
     /* onb.h:8-13 */
@@ -179,6 +179,8 @@ int pto_triangle_hit(const float pos[9], const float uv[6], pto_vec3 o, pto_vec3
     if (t < tmax && t > tmin) {
         rec->hit = 1;
         rec->t = t;
+        rec->bu = u;
+        rec->bv = v;
         rec->p = vadd(o, vscale(d, t));               /* ray.h:19: A + t*B */
         rec->normal = vnormalize(vcross(e1, e2));     /* geometric, never flipped towards the ray */
         if (uv) {
@@ -216,7 +218,7 @@ static v3 triangle_random(const float pos[9], v3 o, rng_ctx *c) {
     v3 random_point = vadd(vadd(vscale(v0, 1 - sqrt_r1), vscale(v1, sqrt_r1 * (1 - r2))), vscale(v2, sqrt_r1 * r2));
     return vsub(random_point, o);
 }
-pto_vec3 pto_triangle_random(const float pos[9], pto_vec3 o, pto_rng *s) { rng_ctx c = {s, NULL}; return triangle_random(pos, o, &c); }
+pto_vec3 pto_triangle_random(const float pos[9], pto_vec3 o, pto_rng *s) { rng_ctx c = {s, NULL, NULL, 0, 0, 0.f}; return triangle_random(pos, o, &c); }
 
 /* ---- sphere (dead code in the reference, live here: SURVEY §8a D1) ---- */
 int pto_sphere_hit(const float sph[4], pto_vec3 o, pto_vec3 d, float tmin, float tmax, pto_hit *rec) {
@@ -231,7 +233,7 @@ int pto_sphere_hit(const float sph[4], pto_vec3 o, pto_vec3 d, float tmin, float
     if (discriminant > 0) {
         float temp = (float)((-b - sqrtf(discriminant)) / (2.0 * a));
         if (temp < tmax && temp > tmin) {
-            rec->hit = 1; rec->t = temp;
+            rec->hit = 1; rec->t = temp; rec->bu = rec->bv = 0.f;
             rec->p = vadd(o, vscale(d, temp));
             rec->normal = vdiv(vsub(rec->p, center), radius);
             rec->u = rec->v = 0.f;
@@ -239,7 +241,7 @@ int pto_sphere_hit(const float sph[4], pto_vec3 o, pto_vec3 d, float tmin, float
         }
         temp = (float)((-b + sqrtf(discriminant)) / (2.0 * a));
         if (temp < tmax && temp > tmin) {
-            rec->hit = 1; rec->t = temp;
+            rec->hit = 1; rec->t = temp; rec->bu = rec->bv = 0.f;
             rec->p = vadd(o, vscale(d, temp));
             rec->normal = vdiv(vsub(rec->p, center), radius);
             rec->u = rec->v = 0.f;
@@ -545,7 +547,18 @@ static v3 ray_color(const pto_world *w, v3 ro, v3 rd, uint32_t depth, rng_ctx *c
     for (uint32_t i = 0; i < depth; i++) {
         pto_hit rec;
         if (st) st->rays++;
-        if (pto_world_hit(w, cur_o, cur_d, 0.001f, FLT_MAX, &rec)) {
+        int got = pto_world_hit(w, cur_o, cur_d, 0.001f, FLT_MAX, &rec);
+        if (c->events) {
+            if (c->n_events < c->max_events) {
+                float *e = c->events + (size_t)c->n_events * 16;
+                e[0] = c->cur_sample; e[1] = (float)i; e[2] = got ? (float)rec.prim : -1.f; e[3] = got ? rec.t : FLT_MAX;
+                e[4] = got ? rec.bu : 0.f; e[5] = got ? rec.bv : 0.f;
+                e[6] = cur_o.x; e[7] = cur_o.y; e[8] = cur_o.z; e[9] = cur_d.x; e[10] = cur_d.y; e[11] = cur_d.z;
+                e[12] = cur_attenuation.x; e[13] = cur_attenuation.y; e[14] = cur_attenuation.z; e[15] = 0.f;
+            }
+            c->n_events++;
+        }
+        if (got) {
             const PtMaterial *m = &w->mats[rec.mat];
             if (m->type == PT_MAT_UNIVERSAL) {
                 /* UniversalMaterial::scatter, material.h:52-78 */
@@ -640,7 +653,7 @@ static v3 ray_color(const pto_world *w, v3 ro, v3 rd, uint32_t depth, rng_ctx *c
 }
 
 pto_vec3 pto_ray_color(const pto_world *w, pto_vec3 o, pto_vec3 d, uint32_t depth, pto_rng *s, pto_stats *st) {
-    rng_ctx c = {s, st};
+    rng_ctx c = {s, st, NULL, 0, 0, 0.f};
     return ray_color(w, o, d, depth, &c);
 }
 
@@ -668,7 +681,7 @@ int pto_render(const pto_world *w, const PtCamera *cam, uint32_t width, uint32_t
                 int32_t pixel_index = ((int32_t)height - y - 1) * (int32_t)width + x;
                 pto_rng rs;
                 pto_rng_init(&rs, (uint64_t)(int64_t)(1984 + pixel_index)); /* render_init, :54 */
-                rng_ctx c = {&rs, &local};
+                rng_ctx c = {&rs, &local, NULL, 0, 0, 0.f};
                 v3 col = V(0, 0, 0);
                 for (uint32_t s = 0; s < spp; s++) {
                     float u = (float)(x + U(&c)) / (float)width;
@@ -708,4 +721,24 @@ int pto_render(const pto_world *w, const PtCamera *cam, uint32_t width, uint32_t
     }
     if (st) *st = total;
     return 0;
+}
+
+int pto_trace_pixel(const pto_world *w, const PtCamera *cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t depth, int32_t x, int32_t y,
+                    float *events, int32_t max_events, float *col_out) {
+    cam_params cp = camera_params(cam);
+    int32_t pixel_index = ((int32_t)height - y - 1) * (int32_t)width + x;
+    pto_rng rs;
+    pto_rng_init(&rs, (uint64_t)(int64_t)(1984 + pixel_index));
+    rng_ctx c = {&rs, NULL, events, max_events, 0, 0.f};
+    v3 col = V(0, 0, 0);
+    for (uint32_t s = 0; s < spp; s++) {
+        float u = (float)(x + U(&c)) / (float)width;
+        float v = (float)(y + U(&c)) / (float)height;
+        v3 ro, rd;
+        camera_get_ray(&cp, u, v, &ro, &rd);
+        c.cur_sample = (float)s;
+        col = vadd(col, ray_color(w, ro, rd, depth, &c));
+    }
+    col_out[0] = col.x; col_out[1] = col.y; col_out[2] = col.z;
+    return c.n_events;
 }

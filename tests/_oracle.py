@@ -21,7 +21,7 @@ class Rng(C.Structure):
 
 
 class Hit(C.Structure):
-    _fields_ = [("hit", C.c_int), ("t", C.c_float), ("p", Vec3), ("normal", Vec3), ("u", C.c_float), ("v", C.c_float), ("mat", C.c_int32), ("prim", C.c_int32)]
+    _fields_ = [("hit", C.c_int), ("t", C.c_float), ("p", Vec3), ("normal", Vec3), ("u", C.c_float), ("v", C.c_float), ("bu", C.c_float), ("bv", C.c_float), ("mat", C.c_int32), ("prim", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -72,6 +72,7 @@ class Oracle:
             "pto_world_n_lights": (C.c_int, [vp]),
             "pto_world_hit": (C.c_int, [vp, Vec3, Vec3, f, f, P(Hit)]),
             "pto_ray_color": (Vec3, [vp, Vec3, Vec3, u32, P(Rng), P(Stats)]),
+            "pto_trace_pixel": (C.c_int, [vp, P(ptb200.PtCamera), u32, u32, u32, u32, i32, i32, vp, i32, vp]),
             "pto_render": (C.c_int, [vp, P(ptb200.PtCamera), u32, u32, u32, u32, i32, i32, i32, i32, vp, vp, vp, P(Stats), C.c_int]),
         }
         for name, (res, args) in sig.items():
@@ -101,6 +102,14 @@ class Oracle:
         assert rc == 0
         out = (rgb, yuv[: width * height * 3 // 2], st.as_dict())
         return out + (acc,) if want_accum else out
+
+
+    def trace_pixel(self, world, width, height, spp, depth, x, y, camera=None, max_events=4096):
+        cam = self.ptb.make_camera(**{**self.ptb.DEFAULT_CAMERA, **(camera or {})})
+        ev = np.zeros((max_events, 16), np.float32)
+        col = np.zeros(3, np.float32)
+        n = self.lib.pto_trace_pixel(world, C.byref(cam), width, height, spp, depth, x, y, ev.ctypes.data, max_events, col.ctypes.data)
+        return ev[: min(n, max_events)], col
 
 
 def load():
