@@ -1,14 +1,33 @@
-"""CUDA path (through the C ABI) against the CPU oracle and against its own exact invariants.  pytest -m gpu.
+"""CUDA path (through the C ABI) against the checkers and against its own exact invariants.  pytest -m gpu.
 
-Tolerances (stream-faithful mode: XORWOW per pixel, same draw order / spp / depth / camera) follow SURVEY §8d:
-the GPU and a CPU evaluate the same float expressions with different contraction / rsqrtf / sinf / cosf, so a
-rounding flip at a silhouette desynchronises that pixel's stream for its remaining samples (probability about
-1.2e-4 per sample).  Hence, with the 8-bit output:
-    fraction of pixels within +-1   >=  1 - 2e-4 * spp - 0.005
-    mean |diff|                     <=  0.25 / 255
-    RMSE                            <=  2 / 255          (spp <= 128)
+Two parity gates (stream-faithful mode: XORWOW per pixel, same draw order / spp / depth / camera):
+
+ A. vs the reference's OWN CUDA renderer (oracle/_ref/ref_gpu: its kernels unmodified, frame >= 2): BIT-EXACT.
+    Checked against fixtures that binary rendered on a B200 (tests/golden/ref_gpu_*.png, oracle/make_golden_gpu.py)
+    and, when the binary travelled to this box, against a live run.
+
+ B. vs the CPU oracle (oracle/pt_oracle.c, itself bit-identical to the host-compiled reference): a stated tolerance,
+    because host and device round differently (FMA contraction, MUFU rsqrt, sinf/cosf).  A one-ulp difference in a
+    hit point decides whether the next ray re-hits its own surface just above t_min = 0.001 (the reference has no
+    ray-offset), which desynchronises that pixel's stream for its remaining samples.  Measured on B200 for the
+    reference's own two builds (CUDA vs host-compiled) and identically for ours: 7.7e-4 .. 9.8e-4 per sample
+    (profiles/r01_parity_probe.json).  Hence, on the 8-bit output:
+        depth <= 2                      bit-exact
+        fraction of pixels within +-1   >=  1 - 1.5e-3 * spp - 0.005
+        mean |diff|                     <=  0.30 / 255
+        RMSE                            <=  4.0 / 255 (spp <= 16),  3.0 / 255 (spp <= 128)
+
 Exact invariants (bit for bit): run-to-run, tile-size/order independence, direct kernel == persistent kernel.
 """
+import gzip
+import json
+import subprocess
+import tempfile
+from pathlib import Path
+
+from PIL import Image
+
+from conftest import GOLD, ROOT
 import numpy as np
 import pytest
 
@@ -20,15 +39,53 @@ def compare(rgb, ref, spp):
     frac1 = float((d.max(axis=2) <= 1).mean())
     mad = float(d.mean())
     rmse = float(np.sqrt((d.astype(np.float64) ** 2).mean()))
-    return dict(frac_within_1=frac1, identical=float((d.max(axis=2) == 0).mean()), mad=mad, rmse=rmse, bound=1 - 2e-4 * spp - 0.005)
+    return dict(frac_within_1=frac1, identical=float((d.max(axis=2) == 0).mean()), mad=mad, rmse=rmse, bound=1 - 1.5e-3 * spp - 0.005)
 
 
 def check(rgb, ref, spp):
     m = compare(rgb, ref, spp)
     assert m["frac_within_1"] >= m["bound"], m
-    assert m["mad"] <= 0.25, m
-    assert m["rmse"] <= 2.0, m
+    assert m["mad"] <= 0.30, m
+    assert m["rmse"] <= (4.0 if spp <= 16 else 3.0), m
     return m
+
+
+def _cam(extra):
+    if not extra:
+        return None
+    v = [float(x) for x in extra[1:9]]
+    return dict(look_from=tuple(v[0:3]), front=tuple(v[3:6]), vfov=v[6], hfov=v[7])
+
+
+REF_GPU_META = json.loads((GOLD / "ref_gpu_images.json").read_text())["images"] if (GOLD / "ref_gpu_images.json").exists() else {}
+
+
+@pytest.mark.parametrize("name", sorted(REF_GPU_META) or ["<no fixtures>"])
+def test_cuda_is_bit_exact_with_reference_cuda_renderer_fixtures(tracer, duck, name):
+    if not REF_GPU_META:
+        pytest.skip("tests/golden/ref_gpu_images.json not generated yet (oracle/make_golden_gpu.py on a GPU box)")
+    m = REF_GPU_META[name]
+    rgb, yuv = render(tracer, duck, m["width"], m["height"], m["spp"], m["depth"], _cam(m["extra"]))
+    ref = np.array(Image.open(GOLD / f"ref_gpu_{name}.png").convert("RGB"))
+    assert np.array_equal(rgb, ref), compare(rgb, ref, m["spp"])
+    ref_yuv = np.frombuffer(gzip.decompress((GOLD / f"ref_gpu_{name}.yuv.gz").read_bytes()), np.uint8)
+    assert np.array_equal(yuv, ref_yuv)
+
+
+def test_cuda_is_bit_exact_with_live_reference_cuda_renderer(tracer, duck):
+    ref_gpu = ROOT / "oracle" / "_ref" / "ref_gpu"
+    if not ref_gpu.exists():
+        pytest.skip("oracle/_ref/ref_gpu did not travel to this box")
+    w, h, spp, depth = 200, 112, 12, 10
+    with tempfile.TemporaryDirectory() as td:
+        flat, ppm = Path(td) / "duck.ptscene", Path(td) / "ref.ppm"
+        flat.write_bytes(duck.to_ptscene_bytes())
+        r = subprocess.run([str(ref_gpu), str(flat), str(w), str(h), str(spp), str(depth), str(ppm)], capture_output=True, text=True, timeout=600)
+        if r.returncode != 0 or "REF_GPU_JSON" not in r.stdout:
+            pytest.skip(f"ref_gpu could not run here: {(r.stderr or r.stdout)[-200:]}")
+        ref = np.array(Image.open(ppm).convert("RGB"))
+    rgb, _ = render(tracer, duck, w, h, spp, depth)
+    assert np.array_equal(rgb, ref), compare(rgb, ref, spp)
 
 
 def render(tracer, scene, w, h, spp, depth, camera=None, kernel=None, ptb=None):
@@ -46,11 +103,14 @@ def render(tracer, scene, w, h, spp, depth, camera=None, kernel=None, ptb=None):
     (64, 48, 16, 3, dict(look_from=(-120.0, 40.0, -300.0), front=(0.25, -0.1, -1.0), vfov=60.0, hfov=80.0)),
     (37, 23, 5, 1, None),   # ragged sizes, depth 1
     (8, 4, 1, 10, None),
+    (160, 90, 3, 2, None),  # depth <= 2: bit-exact (asserted below)
 ])
 def test_cuda_matches_oracle_on_cornell_duck(tracer, oracle, duck, w, h, spp, depth, camera):
     rgb, yuv = render(tracer, duck, w, h, spp, depth, camera)
     ref, ref_yuv, ost = oracle.render(duck, w, h, spp, depth, camera=camera)
     m = check(rgb, ref, spp)
+    if depth <= 2:
+        assert m["identical"] == 1.0, m
     st = tracer.stats()
     assert st["samples"] == w * h * spp
     assert abs(st["rays"] - ost["rays"]) <= 0.01 * ost["rays"] + 8
