@@ -36,8 +36,8 @@ struct RendererConfig {
     bool showTasks = true;
     int kParam = 1;
     // --- additions (defaults keep the reference's behaviour) ---
-    unsigned int dynamicTileWidth = 128;   // DYNAMIC mode tile size
-    unsigned int dynamicTileHeight = 64;
+    unsigned int dynamicTileWidth = 256;   // DYNAMIC mode tile size
+    unsigned int dynamicTileHeight = 128;
     std::string outputPath{};              // FileRenderer: where out.ppm goes (README.md:52-58)
     unsigned int framesToRender = 1;       // FileRenderer stops after this many frames
 };
