@@ -175,7 +175,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="override for quick experiments (a non-default value is flagged in config)")
-    ap.add_argument("--kernel", default="persistent", choices=["persistent", "direct"])
+    ap.add_argument("--kernel", default="persistent", choices=["persistent", "direct", "lockstep"])
+    ap.add_argument("--refill-at", type=int, default=0)
+    ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--tile", default="64x32")
     ap.add_argument("--claim", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -212,7 +214,11 @@ def main():
     pt.upload_scene(scene)
     pt.set_camera()
     pt.set_params(spp, DEPTH)
-    pt.set_option(ptb200.PT_OPT_KERNEL, ptb200.PT_KERNEL_DIRECT if args.kernel == "direct" else ptb200.PT_KERNEL_PERSISTENT)
+    pt.set_option(ptb200.PT_OPT_KERNEL, {"persistent": ptb200.PT_KERNEL_PERSISTENT, "direct": ptb200.PT_KERNEL_DIRECT, "lockstep": ptb200.PT_KERNEL_LOCKSTEP}[args.kernel])
+    if args.refill_at:
+        pt.set_option(ptb200.PT_OPT_REFILL_AT, args.refill_at)
+    if args.blocks_per_sm:
+        pt.set_option(ptb200.PT_OPT_BLOCKS_PER_SM, args.blocks_per_sm)
 
     tw, th = (int(x) for x in args.tile.split("x"))
     if world == 1:
@@ -349,7 +355,7 @@ def main():
         sm_mhz = (clocks or {}).get("sm_mhz") or peaks["sm_max_mhz"]
         fp32_peak_max = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
         roofline = {"bound": "hbm", "achieved": abytes / (kernel_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": abytes / (kernel_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "kernel": "pt_persistent_kernel" if args.kernel == "persistent" else "pt_direct_kernel",
+                    "frac": abytes / (kernel_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "kernel": {"persistent": "pt_wavefront_kernel", "direct": "pt_direct_kernel", "lockstep": "pt_persistent_kernel"}[args.kernel],
                     "peak_source": peaks["source"], "algorithmic_bytes_per_ray": BYTES_PER_RAY(per_ray["box"], per_ray["tri"]),
                     "note": "algorithmic bytes are node/triangle fetches served by L1/L2 on this 1.5 MB scene; the binding roof is FP32 issue (roofline_fp32)"}
         roofline_fp32 = {"bound": "fp32", "achieved": aflops / (kernel_ms / 1e3) / 1e12, "peak": fp32_peak_max, "unit": "TFLOP/s",

@@ -103,11 +103,12 @@ enum { /* ptcore_set_option keys */
     PT_OPT_BVH_LEAF_MAX = 3, /* max triangles per leaf for the next upload (default 4) */
     PT_OPT_BLOCKS_PER_SM = 4,/* persistent grid = SMs x this (0 = auto) */
     PT_OPT_SLICE_SPP = 5,    /* samples a lane runs on one pixel before handing it back to the pool (0 = whole pixel) */
-    PT_OPT_BVH_REFERENCE_LIKE = 6 /* 1: build the tree with the reference's own heuristic (attribution runs only) */
+    PT_OPT_REFILL_AT = 6     /* wavefront kernel: finished lanes per warp that trigger a shade/refill pass (1..32, default 12) */
 };
 enum {
-    PT_KERNEL_PERSISTENT = 0, /* persistent-thread wavefront (default) */
-    PT_KERNEL_DIRECT = 1      /* one thread per pixel, no refill: the plain parity slice */
+    PT_KERNEL_PERSISTENT = 0, /* persistent-thread wavefront: per-lane pixel refill + warp-voted uniform traversal steps (default) */
+    PT_KERNEL_DIRECT = 1,     /* one thread per pixel, no refill: the plain parity slice */
+    PT_KERNEL_LOCKSTEP = 2    /* persistent threads with per-lane refill but a per-lane traversal loop (A/B baseline) */
 };
 
 typedef struct PtStats {
@@ -168,6 +169,11 @@ int ptcore_reset_stats(ptcore_t *h);
  *      direction xyz, throughput xyz before shading, 0.  col receives the un-quantised pixel sum. ---- */
 int ptcore_debug_trace_pixel(ptcore_t *h, uint32_t width, uint32_t height, int32_t x, int32_t y, float *events, int32_t max_events,
                              int32_t *n_events, float *col);
+
+/* Host-only structural self-test of the scene compiler: builds the BVH for `scene` exactly as ptcore_upload_scene does and
+ * validates it (every primitive in exactly one leaf, child boxes inside parents and around their primitives, references in
+ * range, depth within the device stack, leaves <= leaf_max).  Needs no GPU.  msg receives the reason on failure. */
+int pt_bvh_selftest(const PtSceneDesc *scene, int32_t leaf_max, PtStats *out, char *msg, size_t msg_len);
 
 /* ---- multi-GPU plumbing: a tile counter shared by the ranks of one node (POSIX shared memory).
  *      Replaces the per-frame static rectangles of RenderManager/TaskGenerator

@@ -20,8 +20,8 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "_lib" / "libptcore.so"
 
 PT_MAT_LAMBERTIAN, PT_MAT_METAL, PT_MAT_DIELECTRIC, PT_MAT_DIFFUSE_LIGHT, PT_MAT_UNIVERSAL = range(5)
-PT_OPT_KERNEL, PT_OPT_COUNT_TESTS, PT_OPT_BVH_LEAF_MAX, PT_OPT_BLOCKS_PER_SM, PT_OPT_SLICE_SPP, PT_OPT_BVH_REFERENCE_LIKE = range(1, 7)
-PT_KERNEL_PERSISTENT, PT_KERNEL_DIRECT = 0, 1
+PT_OPT_KERNEL, PT_OPT_COUNT_TESTS, PT_OPT_BVH_LEAF_MAX, PT_OPT_BLOCKS_PER_SM, PT_OPT_SLICE_SPP, PT_OPT_REFILL_AT = range(1, 7)
+PT_KERNEL_PERSISTENT, PT_KERNEL_DIRECT, PT_KERNEL_LOCKSTEP = 0, 1, 2
 
 
 class PtError(RuntimeError):
@@ -200,6 +200,7 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         "ptcore_get_stats": (C.c_int, [vp, C.POINTER(PtStats)]),
         "ptcore_reset_stats": (C.c_int, [vp]),
         "ptcore_debug_trace_pixel": (C.c_int, [vp, u32, u32, i32, i32, vp, i32, C.POINTER(i32), vp]),
+        "pt_bvh_selftest": (C.c_int, [C.POINTER(PtSceneDesc), i32, C.POINTER(PtStats), C.c_char_p, C.c_size_t]),
         "pt_tileq_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
         "pt_tileq_claim": (i64, [vp, i64, i64]),
         "pt_tileq_reset": (C.c_int, [vp]),
@@ -355,6 +356,15 @@ class PathTracer:
 
     def reset_stats(self) -> None:
         self._ck(self.lib.ptcore_reset_stats(self.h))
+
+
+def bvh_selftest(scene: Scene, leaf_max: int = 4):
+    """(ok, message, stats) of the host-only BVH build + validation (no GPU needed)."""
+    d, keep = scene.desc()
+    st = PtStats()
+    msg = C.create_string_buffer(256)
+    rc = load_library().pt_bvh_selftest(C.byref(d), leaf_max, C.byref(st), msg, 256)
+    return rc == 0, msg.value.decode(), st.as_dict()
 
 
 def write_ppm(path, rgb: np.ndarray) -> None:

@@ -62,6 +62,8 @@ struct RenderParams {
     DevScene scene;
     CamParams cam;
     uint32_t width, height, spp, depth;
+    int32_t refill_at;  // wavefront kernel: finished lanes per warp that trigger a shade/refill pass (1..32)
+    int32_t pad0;
     uint8_t *fb_rgb, *fb_yuv;
     uint32_t *work_counter;
     DevCounters *counters;
@@ -274,6 +276,108 @@ __device__ __forceinline__ Hit closest_hit(const DevScene &sc, float3 o, float3 
         node = stack[--sp];
     }
     return best;
+}
+
+// ----------------------------------------------------------------------------------------
+// resumable traversal: the same closest-hit search cut into uniform STEPS so that a warp can run
+// "everyone who is at an inner node takes one node step" / "everyone who holds a leaf primitive
+// tests one primitive" under warp votes (pt_wavefront_kernel).  A lane may hold one postponed
+// leaf while it keeps descending, so node steps and primitive steps batch up across the warp.
+// ----------------------------------------------------------------------------------------
+constexpr int32_t kTravDone = 0x7fffffff;  // `cur` when the stack ran empty
+
+struct Trav {
+    int32_t cur;        // >= 0 inner node, < 0 leaf reference, kTravDone = nothing left to visit
+    int32_t leaf_next;  // next primitive of the postponed leaf (leaf-order position)
+    int32_t leaf_left;  // primitives of the postponed leaf still to test (0 = no leaf held)
+    int32_t sp;
+    float3 inv, oinv;
+    Hit best;
+};
+
+__device__ __forceinline__ void trav_begin(Trav &t, float3 o, float3 d) {
+    t.cur = 0;
+    t.leaf_next = 0;
+    t.leaf_left = 0;
+    t.sp = 0;
+    t.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    t.oinv = f3(-o.x * t.inv.x, -o.y * t.inv.y, -o.z * t.inv.z);
+    t.best.t = FLT_MAX;
+    t.best.u = t.best.v = 0.f;
+    t.best.prim = -1;
+}
+__device__ __forceinline__ bool trav_at_inner(const Trav &t) { return t.cur >= 0 && t.cur != kTravDone; }
+__device__ __forceinline__ bool trav_has_leaf(const Trav &t) { return t.leaf_left > 0; }
+__device__ __forceinline__ bool trav_finished(const Trav &t) { return t.cur == kTravDone && t.leaf_left == 0; }
+
+// moves a leaf reference sitting in `cur` into the postponed-leaf slot (if free) and pops the next node
+__device__ __forceinline__ void trav_postpone(Trav &t, const int32_t *stack) {
+    if (t.cur < 0 && t.leaf_left == 0) {
+        const int32_t v = ~t.cur;
+        t.leaf_next = v >> 3;
+        t.leaf_left = (v & 7) + 1;
+        t.cur = t.sp > 0 ? stack[--t.sp] : kTravDone;
+    }
+}
+
+// one inner-node step (precondition: trav_at_inner)
+template <bool COUNT>
+__device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, int32_t *stack, float tmin, uint32_t &n_box) {
+    const float kSlack = 1.0000004f;
+    const int32_t node = t.cur;
+    const float4 bx = __ldg(&sc.nodes[node * 4 + 0]);
+    const float4 by = __ldg(&sc.nodes[node * 4 + 1]);
+    const float4 bz = __ldg(&sc.nodes[node * 4 + 2]);
+    const int4 refs = __ldg(reinterpret_cast<const int4 *>(&sc.nodes[node * 4 + 3]));
+    if (COUNT) n_box += 2;
+    float lx0 = fmaf(bx.x, t.inv.x, t.oinv.x), lx1 = fmaf(bx.y, t.inv.x, t.oinv.x);
+    float ly0 = fmaf(by.x, t.inv.y, t.oinv.y), ly1 = fmaf(by.y, t.inv.y, t.oinv.y);
+    float lz0 = fmaf(bz.x, t.inv.z, t.oinv.z), lz1 = fmaf(bz.y, t.inv.z, t.oinv.z);
+    float ln = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), tmin));
+    float lf = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), t.best.t));
+    float rx0 = fmaf(bx.z, t.inv.x, t.oinv.x), rx1 = fmaf(bx.w, t.inv.x, t.oinv.x);
+    float ry0 = fmaf(by.z, t.inv.y, t.oinv.y), ry1 = fmaf(by.w, t.inv.y, t.oinv.y);
+    float rz0 = fmaf(bz.z, t.inv.z, t.oinv.z), rz1 = fmaf(bz.w, t.inv.z, t.oinv.z);
+    float rn = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), tmin));
+    float rf = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), t.best.t));
+    const bool hl = ln <= lf * kSlack;
+    const bool hr = rn <= rf * kSlack;
+    const bool leftFirst = ln <= rn;
+    const int32_t nearRef = (hl & hr) ? (leftFirst ? refs.x : refs.y) : (hl ? refs.x : refs.y);
+    const int32_t farRef = leftFirst ? refs.y : refs.x;
+    if (hl & hr) stack[t.sp++] = farRef;
+    if (hl | hr) t.cur = nearRef;
+    else t.cur = t.sp > 0 ? stack[--t.sp] : kTravDone;
+    trav_postpone(t, stack);
+}
+
+// one primitive of the postponed leaf (precondition: trav_has_leaf)
+template <bool SPHERES, bool COUNT>
+__device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, const int32_t *stack, float3 o, float3 d, float tmin, uint32_t &n_tri) {
+    const int32_t k = t.leaf_next;
+    const float4 q0 = __ldg(&sc.prims[k * 3 + 0]);
+    const float4 q1 = __ldg(&sc.prims[k * 3 + 1]);
+    const float4 q2 = __ldg(&sc.prims[k * 3 + 2]);
+    if (COUNT) n_tri += 1;
+    if (SPHERES && __float_as_int(q2.z) == 1) {
+        float tt;
+        if (sphere_test(f3(q0.x, q0.y, q0.z), q0.w, o, d, tmin, t.best.t, tt)) {
+            t.best.t = tt;
+            t.best.u = t.best.v = 0.f;
+            t.best.prim = k;
+        }
+    } else {
+        float tt, u, w;
+        if (triangle_test(f3(q0.x, q0.y, q0.z), f3(q0.w, q1.x, q1.y), f3(q1.z, q1.w, q2.x), o, d, tmin, t.best.t, tt, u, w)) {
+            t.best.t = tt;
+            t.best.u = u;
+            t.best.v = w;
+            t.best.prim = k;
+        }
+    }
+    t.leaf_next = k + 1;
+    t.leaf_left -= 1;
+    if (t.leaf_left == 0) trav_postpone(t, stack);  // a second leaf may have been waiting in `cur`
 }
 
 // ----------------------------------------------------------------------------------------

@@ -149,6 +149,133 @@ __global__ void __launch_bounds__(kBlockThreads) pt_persistent_kernel(const __gr
     }
 }
 
+// pt_wavefront_kernel — the default.  Same per-lane pixel ownership and refill as pt_persistent_kernel, but the
+// TRAVERSE stage is a warp-synchronous wavefront over uniform steps (pt_device.cuh: trav_node_step /
+// trav_prim_step): every iteration the warp votes and executes ONE kind of step for all lanes that can take it,
+//       #lanes at an inner node  >=  #lanes holding a leaf primitive   ->  node step      else  primitive step,
+// so box tests and Moeller-Trumbore tests each run with most of the warp instead of a handful of lanes
+// (ncu on pt_persistent_kernel: 7.0 threads per executed instruction, 3.2 inside the triangle test;
+// profiles/r01_ncu_persistent_lockstep.txt).  Lanes whose ray is finished wait; once `refill_at` of them are
+// waiting the warp leaves TRAVERSE, shades exactly those lanes (they get their bounce ray or the next camera
+// ray) and re-enters with the unfinished lanes resuming where they stopped — warp-level ray compaction without
+// moving any state between lanes, which the one-XORWOW-stream-per-pixel contract forbids.
+template <bool SPHERES, bool RTOW, bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads) pt_wavefront_kernel(const __grid_constant__ RenderParams p) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t total_items = p.tiles.first_item[p.tiles.n];
+    const int refill_at = p.refill_at;
+
+    bool retired = false, have_pixel = false, have_path = false;
+    int px = 0, py = 0, pixel_index = 0;
+    uint32_t samples_done = 0, bounce = 0;
+    Rng rng;
+    rng_init(rng, 0);
+    float3 col = f3(0.f, 0.f, 0.f), att = f3(1.f, 1.f, 1.f), ro = f3(0.f, 0.f, 0.f), rd = f3(0.f, 0.f, 1.f);
+    uint32_t n_rays = 0, n_box = 0, n_tri = 0, n_light = 0;
+    unsigned long long acc_box = 0, acc_tri = 0, acc_light = 0;
+    Trav tr;
+    trav_begin(tr, ro, rd);
+    tr.cur = kTravDone;
+    int32_t stack[kStackSize];
+
+    for (;;) {
+        // ---------------- GENERATE / COMPACT ----------------
+        if (!have_path && have_pixel && samples_done == p.spp) {
+            store_pixel(p, pixel_index, col);
+            have_pixel = false;
+        }
+        const bool need = !retired && !have_pixel;
+        const unsigned need_mask = __ballot_sync(kFullMask, need);
+        if (need_mask) {
+            const int leader = __ffs((int)need_mask) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(p.work_counter, (uint32_t)__popc(need_mask));
+            base = __shfl_sync(kFullMask, base, leader);
+            if (need) {
+                const uint32_t item = base + (uint32_t)__popc(need_mask & ((1u << lane) - 1u));
+                if (item >= total_items) {
+                    retired = true;
+                } else if (item_to_pixel(p.tiles, item, px, py)) {
+                    pixel_index = ((int)p.height - py - 1) * (int)p.width + px;
+                    rng_init(rng, (unsigned long long)(long long)(1984 + pixel_index));
+                    col = f3(0.f, 0.f, 0.f);
+                    samples_done = 0;
+                    have_pixel = true;
+                }
+            }
+        }
+        if (__all_sync(kFullMask, retired)) break;
+
+        if (!have_path && have_pixel && samples_done < p.spp) {
+            float u = float(px + rng_uniform(rng)) / float(p.width);
+            float v = float(py + rng_uniform(rng)) / float(p.height);
+            camera_ray(p.cam, u, v, ro, rd);
+            att = f3(1.0f, 1.0f, 1.0f);
+            bounce = 0;
+            have_path = true;
+            trav_begin(tr, ro, rd);
+            n_rays++;
+            if (p.depth == 0) {
+                have_path = false;
+                samples_done++;
+                n_rays--;
+            }
+        }
+
+        // ---------------- TRAVERSE (warp-synchronous wavefront over uniform steps) ----------------
+        for (;;) {
+            const bool work = have_path && !trav_finished(tr);
+            const bool can_node = work && trav_at_inner(tr);
+            const bool can_prim = work && trav_has_leaf(tr);
+            const unsigned m_node = __ballot_sync(kFullMask, can_node);
+            const unsigned m_prim = __ballot_sync(kFullMask, can_prim);
+            if ((m_node | m_prim) == 0) break;
+            const unsigned m_wait = __ballot_sync(kFullMask, have_path && !work);
+            if (__popc(m_wait) >= refill_at) break;
+            if (__popc(m_node) >= __popc(m_prim)) {
+                if (can_node) trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
+            } else {
+                if (can_prim) trav_prim_step<SPHERES, COUNT>(p.scene, tr, stack, ro, rd, 0.001f, n_tri);
+            }
+        }
+
+        // ---------------- SHADE (only lanes whose ray is finished) ----------------
+        if (have_path && trav_finished(tr)) {
+            float3 contrib;
+            bool cont = shade<SPHERES, RTOW, COUNT>(p.scene, tr.best, ro, rd, att, rng, contrib, n_light);
+            bounce++;
+            if (cont && bounce < p.depth) {
+                trav_begin(tr, ro, rd);
+                n_rays++;
+            } else {
+                col = col + (cont ? f3(0.0f, 0.0f, 0.0f) : contrib);  // camera.h:82 exhausted -> (0,0,0)
+                have_path = false;
+                samples_done++;
+            }
+        }
+        if (COUNT) {
+            acc_box += n_box; acc_tri += n_tri; acc_light += n_light;
+            n_box = n_tri = n_light = 0;
+        }
+    }
+
+    unsigned long long r = n_rays;
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(kFullMask, r, o);
+    if (lane == 0 && r) atomicAdd(&p.counters->rays, r);
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            acc_box += __shfl_down_sync(kFullMask, acc_box, o);
+            acc_tri += __shfl_down_sync(kFullMask, acc_tri, o);
+            acc_light += __shfl_down_sync(kFullMask, acc_light, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&p.counters->box_tests, acc_box);
+            atomicAdd(&p.counters->tri_tests, acc_tri);
+            atomicAdd(&p.counters->light_tests, acc_light);
+        }
+    }
+}
+
 // One thread per pixel of ONE tile (tiles.n == 1), 8x4 blocks per warp, no refill.
 template <bool SPHERES, bool RTOW, bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads) pt_direct_kernel(const __grid_constant__ RenderParams p) {

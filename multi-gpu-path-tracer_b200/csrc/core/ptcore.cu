@@ -67,6 +67,7 @@ struct ptcore {
     int leaf_max = 4;
     int blocks_per_sm = 0;
     int slice_spp = 0;
+    int refill_at = 12;
 
     PtStats build_stats{};
 };
@@ -106,6 +107,35 @@ float triangle_area_host(const float *p) {
     return sqrtf(d) * 0.5f;
 }
 
+// bounds of every primitive, padded: the slab test must never cull a hit the primitive test accepts
+std::vector<PrimBounds> padded_bounds(const PtSceneDesc *sc) {
+    const int64_t n_prims = (int64_t)sc->n_tris + sc->n_spheres;
+    std::vector<PrimBounds> pb((size_t)n_prims);
+    for (int32_t i = 0; i < sc->n_tris; i++) {
+        const float *p = sc->tri_pos + (size_t)i * 9;
+        for (int k = 0; k < 3; k++) {
+            pb[(size_t)i].lo[k] = std::min(p[k], std::min(p[3 + k], p[6 + k]));
+            pb[(size_t)i].hi[k] = std::max(p[k], std::max(p[3 + k], p[6 + k]));
+        }
+    }
+    for (int32_t i = 0; i < sc->n_spheres; i++) {
+        const float *s = sc->sph + (size_t)i * 4;
+        float r = std::fabs(s[3]);
+        for (int k = 0; k < 3; k++) {
+            pb[(size_t)sc->n_tris + (size_t)i].lo[k] = s[k] - r;
+            pb[(size_t)sc->n_tris + (size_t)i].hi[k] = s[k] + r;
+        }
+    }
+    for (auto &b : pb)
+        for (int k = 0; k < 3; k++) {
+            float m = std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
+            float e = m * 1e-5f + 1e-6f;
+            b.lo[k] -= e;
+            b.hi[k] += e;
+        }
+    return pb;
+}
+
 template <bool S, bool R, bool C>
 cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaStream_t stream) {
     const uint32_t total = rp.tiles.first_item[rp.tiles.n];
@@ -115,14 +145,16 @@ cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaS
         pt_direct_kernel<S, R, C><<<grid, kBlockThreads, 0, stream>>>(rp);
     } else {
         int occ = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_persistent_kernel<S, R, C>, kBlockThreads, 0);
+        cudaError_t e = h->kernel == PT_KERNEL_LOCKSTEP ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_persistent_kernel<S, R, C>, kBlockThreads, 0)
+                                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_wavefront_kernel<S, R, C>, kBlockThreads, 0);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
         if (h->blocks_per_sm > 0) occ = std::min(occ, h->blocks_per_sm);
         uint32_t grid = (uint32_t)h->sm_count * (uint32_t)occ;
         uint32_t needed = (total + kBlockThreads - 1) / kBlockThreads;
         if (grid > needed) grid = needed;
-        pt_persistent_kernel<S, R, C><<<grid, kBlockThreads, 0, stream>>>(rp);
+        if (h->kernel == PT_KERNEL_LOCKSTEP) pt_persistent_kernel<S, R, C><<<grid, kBlockThreads, 0, stream>>>(rp);
+        else pt_wavefront_kernel<S, R, C><<<grid, kBlockThreads, 0, stream>>>(rp);
     }
     return cudaGetLastError();
 }
@@ -171,6 +203,8 @@ int render_tiles(ptcore *h, const PtTile *tiles, int32_t n_tiles, cudaStream_t s
         rp.height = h->fb_h;
         rp.spp = h->spp;
         rp.depth = h->depth;
+        rp.refill_at = h->refill_at;
+        rp.pad0 = 0;
         rp.fb_rgb = h->fb_rgb;
         rp.fb_yuv = h->fb_yuv;
         rp.counters = h->d_counters;
@@ -271,30 +305,7 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
     PT_CUDA(h, cudaSetDevice(h->device));
     auto t0 = std::chrono::high_resolution_clock::now();
 
-    // ---- bounds (padded: the slab test must never cull a hit the primitive test accepts) ----
-    std::vector<PrimBounds> pb((size_t)n_prims);
-    for (int32_t i = 0; i < sc->n_tris; i++) {
-        const float *p = sc->tri_pos + (size_t)i * 9;
-        for (int k = 0; k < 3; k++) {
-            pb[(size_t)i].lo[k] = std::min(p[k], std::min(p[3 + k], p[6 + k]));
-            pb[(size_t)i].hi[k] = std::max(p[k], std::max(p[3 + k], p[6 + k]));
-        }
-    }
-    for (int32_t i = 0; i < sc->n_spheres; i++) {
-        const float *s = sc->sph + (size_t)i * 4;
-        float r = std::fabs(s[3]);
-        for (int k = 0; k < 3; k++) {
-            pb[(size_t)sc->n_tris + (size_t)i].lo[k] = s[k] - r;
-            pb[(size_t)sc->n_tris + (size_t)i].hi[k] = s[k] + r;
-        }
-    }
-    for (auto &b : pb)
-        for (int k = 0; k < 3; k++) {
-            float m = std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
-            float e = m * 1e-5f + 1e-6f;
-            b.lo[k] -= e;
-            b.hi[k] += e;
-        }
+    std::vector<PrimBounds> pb = padded_bounds(sc);
 
     BvhBuildOptions opt;
     opt.leaf_max = h->leaf_max;
@@ -463,7 +474,7 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
     if (!h) return PT_ERR_INVALID_ARGUMENT;
     switch (key) {
         case PT_OPT_KERNEL:
-            if (value != PT_KERNEL_PERSISTENT && value != PT_KERNEL_DIRECT) return fail(h, PT_ERR_INVALID_ARGUMENT, "unknown kernel");
+            if (value != PT_KERNEL_PERSISTENT && value != PT_KERNEL_DIRECT && value != PT_KERNEL_LOCKSTEP) return fail(h, PT_ERR_INVALID_ARGUMENT, "unknown kernel");
             h->kernel = (int)value;
             return PT_OK;
         case PT_OPT_COUNT_TESTS: h->count_tests = value != 0; return PT_OK;
@@ -474,6 +485,10 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
         case PT_OPT_BLOCKS_PER_SM:
             if (value < 0 || value > 32) return fail(h, PT_ERR_INVALID_ARGUMENT, "blocks_per_sm must be in [0, 32]");
             h->blocks_per_sm = (int)value;
+            return PT_OK;
+        case PT_OPT_REFILL_AT:
+            if (value < 1 || value > 32) return fail(h, PT_ERR_INVALID_ARGUMENT, "refill_at must be in [1, 32]");
+            h->refill_at = (int)value;
             return PT_OK;
         case PT_OPT_SLICE_SPP:
             if (value != 0) return fail(h, PT_ERR_UNSUPPORTED, "sample slicing is not implemented yet");
@@ -604,6 +619,34 @@ int ptcore_debug_trace_pixel(ptcore_t *h, uint32_t width, uint32_t height, int32
     cudaFree(d_events); cudaFree(d_col); cudaFree(d_n);
     if (e != cudaSuccess) return fail(h, (int)e, std::string("ptcore_debug_trace_pixel: ") + cudaGetErrorString(e));
     return PT_OK;
+}
+
+int pt_bvh_selftest(const PtSceneDesc *sc, int32_t leaf_max, PtStats *out, char *msg, size_t msg_len) {
+    if (!sc || sc->n_tris < 0 || sc->n_spheres < 0) return PT_ERR_INVALID_ARGUMENT;
+    std::vector<PrimBounds> pb = padded_bounds(sc);
+    BvhBuildOptions opt;
+    opt.leaf_max = leaf_max > 0 ? leaf_max : 4;
+    BvhBuildResult bvh = build_bvh(pb, opt);
+    const char *why = validate_bvh(bvh, pb);
+    if (msg && msg_len) snprintf(msg, msg_len, "%s", why);
+    if (out) {
+        memset(out, 0, sizeof *out);
+        out->bvh_nodes = (uint32_t)bvh.nodes.size();
+        out->bvh_leaves = bvh.n_leaves;
+        out->bvh_depth = bvh.depth;
+        out->bvh_build_ms = bvh.build_ms;
+        out->sah_cost = bvh.sah_cost;
+        out->scene_bytes = bvh.nodes.size() * sizeof(FlatNode);
+    }
+    int max_leaf = 0;
+    for (const FlatNode &n : bvh.nodes)
+        for (int32_t ref : {n.left, n.right})
+            if (ref < 0) max_leaf = std::max(max_leaf, (int)((~ref) & (kMaxLeafPrims - 1)) + 1);
+    if (why[0] == 0 && !pb.empty() && max_leaf > std::max(1, std::min((int)opt.leaf_max, kMaxLeafPrims))) {
+        if (msg && msg_len) snprintf(msg, msg_len, "leaf with %d primitives exceeds leaf_max", max_leaf);
+        return PT_ERR_SYSTEM;
+    }
+    return why[0] == 0 ? PT_OK : PT_ERR_SYSTEM;
 }
 
 int pt_write_ppm(const char *path, const uint8_t *rgb, uint32_t width, uint32_t height) {

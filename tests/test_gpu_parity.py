@@ -51,6 +51,15 @@ def check(rgb, ref, spp):
     return m
 
 
+def render(tracer, scene, w, h, spp, depth, camera=None, kernel=None, ptb=None):
+    tracer.upload_scene(scene)
+    tracer.set_camera(**(camera or {}))
+    tracer.set_params(spp, depth)
+    if kernel is not None:
+        tracer.set_option(ptb.PT_OPT_KERNEL, kernel)
+    return tracer.render_frame_host(w, h)
+
+
 def _cam(extra):
     if not extra:
         return None
@@ -126,6 +135,12 @@ def test_direct_kernel_equals_persistent_kernel(tracer, duck, ptb):
     a, ya = render(tracer, duck, 120, 68, 6, 6, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
     b, yb = render(tracer, duck, 120, 68, 6, 6, kernel=ptb.PT_KERNEL_DIRECT, ptb=ptb)
     assert np.array_equal(a, b) and np.array_equal(ya, yb)
+    c, yc = render(tracer, duck, 120, 68, 6, 6, kernel=ptb.PT_KERNEL_LOCKSTEP, ptb=ptb)
+    assert np.array_equal(a, c) and np.array_equal(ya, yc)
+    for refill_at in (1, 5, 32):  # the refill threshold only changes scheduling, never pixels
+        tracer.set_option(ptb.PT_OPT_REFILL_AT, refill_at)
+        d, yd = render(tracer, duck, 120, 68, 6, 6, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
+        assert np.array_equal(a, d) and np.array_equal(ya, yd)
 
 
 def test_run_to_run_determinism_and_tile_invariance(tracer, duck, ptb):
