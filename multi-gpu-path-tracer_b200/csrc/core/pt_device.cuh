@@ -487,8 +487,11 @@ __device__ __forceinline__ void store_pixel(const RenderParams &p, int pixel_ind
             int totalPixels = (int)(p.width * p.height);
             int uvSize = totalPixels / 4;
             int uvIndex = (blockRow / 2) * ((int)p.width / 2) + (blockCol / 2);
-            p.fb_yuv[totalPixels + uvIndex] = (uint8_t)(((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128);
-            p.fb_yuv[totalPixels + uvSize + uvIndex] = (uint8_t)(((112 * r - 94 * g - 18 * b + 128) >> 8) + 128);
+            // With an odd width or height the reference's index runs past its own W*H + 2*(W*H/4) byte buffer
+            // (undefined behaviour there); writes that would leave that buffer are dropped here.
+            const int limit = totalPixels + 2 * uvSize;
+            if (totalPixels + uvIndex < limit) p.fb_yuv[totalPixels + uvIndex] = (uint8_t)(((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128);
+            if (totalPixels + uvSize + uvIndex < limit) p.fb_yuv[totalPixels + uvSize + uvIndex] = (uint8_t)(((112 * r - 94 * g - 18 * b + 128) >> 8) + 128);
         }
     }
 }

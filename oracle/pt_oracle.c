@@ -706,8 +706,10 @@ int pto_render(const pto_world *w, const PtCamera *cam, uint32_t width, uint32_t
                         int totalPixels = (int)(width * height);
                         int uvSize = totalPixels / 4;
                         int uvIndex = (blockRow / 2) * ((int)width / 2) + (blockCol / 2);
-                        yuv[totalPixels + uvIndex] = Uc;
-                        yuv[totalPixels + uvSize + uvIndex] = Vc;
+                        /* odd width/height: the reference's index leaves its own W*H + 2*(W*H/4) buffer (UB); dropped */
+                        int limit = totalPixels + 2 * uvSize;
+                        if (totalPixels + uvIndex < limit) yuv[totalPixels + uvIndex] = Uc;
+                        if (totalPixels + uvSize + uvIndex < limit) yuv[totalPixels + uvSize + uvIndex] = Vc;
                     }
                 }
             }

@@ -111,7 +111,7 @@ int main(int argc, char **argv) {
         cam_obj->recalculate_camera_params(cfg);
     }
 
-    std::vector<uint8_t> fb_rgb((size_t)W * (size_t)H * 3, 0), fb_yuv((size_t)W * (size_t)H * 3 / 2 + 2, 0);
+    std::vector<uint8_t> fb_rgb((size_t)W * (size_t)H * 3, 0), fb_yuv((size_t)W * (size_t)H * 3 / 2 + (size_t)W + (size_t)H + 64, 0);  // slack: odd sizes overrun the reference's own layout
     Resolution res{(unsigned)W, (unsigned)H};
 
     omp_set_num_threads(threads);
