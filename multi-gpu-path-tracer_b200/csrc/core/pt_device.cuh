@@ -199,6 +199,21 @@ __device__ __forceinline__ bool sphere_test(float3 center, float radius, float3 
 // ----------------------------------------------------------------------------------------
 constexpr int kStackSize = 48;
 
+// Reciprocal direction for the fma-form slab test t = b * inv + (-o * inv).  A zero (or denormal) direction
+// component would give inv = inf and then inf - inf = NaN exactly when the origin lies between the slab planes,
+// which min/max would turn into "box missed" — culling a box that holds a valid hit (seen on B200 as 2 wrong
+// pixels in the 64x48 camera fixture: primary rays with d.y == 0).  Components are therefore clamped away from
+// zero to 2^-80 (sign kept); the slab distances then belong to a ray that is off by < 1e-18 scene units over any
+// t the scene allows, far inside the boxes' host-side padding, so the test stays conservative.  Only the BOX
+// tests see this: the primitive tests use the unmodified direction, as the reference does.
+__device__ __forceinline__ float3 slab_inverse(float3 d) {
+    const float kTiny = 8.271806125530277e-25f;  // 2^-80
+    const float dx = fabsf(d.x) < kTiny ? copysignf(kTiny, d.x) : d.x;
+    const float dy = fabsf(d.y) < kTiny ? copysignf(kTiny, d.y) : d.y;
+    const float dz = fabsf(d.z) < kTiny ? copysignf(kTiny, d.z) : d.z;
+    return f3(1.0f / dx, 1.0f / dy, 1.0f / dz);
+}
+
 template <bool SPHERES, bool COUNT>
 __device__ __forceinline__ Hit closest_hit(const DevScene &sc, float3 o, float3 d, float tmin, uint32_t &n_box, uint32_t &n_tri) {
     Hit best;
@@ -206,7 +221,7 @@ __device__ __forceinline__ Hit closest_hit(const DevScene &sc, float3 o, float3 
     best.u = best.v = 0.f;
     best.prim = -1;
 
-    const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const float3 inv = slab_inverse(d);
     const float3 oinv = f3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
     const float kSlack = 1.0000004f;  // boxes are padded on the host; this covers the fma rounding of the slab distances
 
@@ -300,7 +315,7 @@ __device__ __forceinline__ void trav_begin(Trav &t, float3 o, float3 d) {
     t.leaf_next = 0;
     t.leaf_left = 0;
     t.sp = 0;
-    t.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    t.inv = slab_inverse(d);
     t.oinv = f3(-o.x * t.inv.x, -o.y * t.inv.y, -o.z * t.inv.z);
     t.best.t = FLT_MAX;
     t.best.u = t.best.v = 0.f;

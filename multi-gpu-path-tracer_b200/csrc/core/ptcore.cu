@@ -67,7 +67,7 @@ struct ptcore {
     int leaf_max = 4;
     int blocks_per_sm = 0;
     int slice_spp = 0;
-    int refill_at = 12;
+    int refill_at = 16;
 
     PtStats build_stats{};
 };

