@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--kernel", default="persistent", choices=["persistent", "direct", "lockstep"])
     ap.add_argument("--refill-at", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
+    ap.add_argument("--node-burst", type=int, default=0)
+    ap.add_argument("--min-blocks", type=int, default=0)
     ap.add_argument("--tile", default="64x32")
     ap.add_argument("--claim", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -219,6 +221,10 @@ def main():
         pt.set_option(ptb200.PT_OPT_REFILL_AT, args.refill_at)
     if args.blocks_per_sm:
         pt.set_option(ptb200.PT_OPT_BLOCKS_PER_SM, args.blocks_per_sm)
+    if args.node_burst:
+        pt.set_option(ptb200.PT_OPT_NODE_BURST, args.node_burst)
+    if args.min_blocks:
+        pt.set_option(ptb200.PT_OPT_MIN_BLOCKS, args.min_blocks)
 
     tw, th = (int(x) for x in args.tile.split("x"))
     if world == 1:

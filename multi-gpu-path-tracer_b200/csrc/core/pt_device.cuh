@@ -62,8 +62,8 @@ struct RenderParams {
     DevScene scene;
     CamParams cam;
     uint32_t width, height, spp, depth;
-    int32_t refill_at;  // wavefront kernel: finished lanes per warp that trigger a shade/refill pass (1..32)
-    int32_t pad0;
+    int32_t refill_at;   // wavefront kernel: finished lanes per warp that trigger a shade/refill pass (1..32)
+    int32_t node_burst;  // wavefront kernel: node steps taken per vote (1..4)
     uint8_t *fb_rgb, *fb_yuv;
     uint32_t *work_counter;
     DevCounters *counters;
@@ -299,43 +299,45 @@ __device__ __forceinline__ Hit closest_hit(const DevScene &sc, float3 o, float3 
 // tests one primitive" under warp votes (pt_wavefront_kernel).  A lane may hold one postponed
 // leaf while it keeps descending, so node steps and primitive steps batch up across the warp.
 // ----------------------------------------------------------------------------------------
-constexpr int32_t kTravDone = 0x7fffffff;  // `cur` when the stack ran empty
+constexpr int32_t kTravDone = (int32_t)0x80000000;  // `cur` when nothing is left to visit: negative, but never a valid leaf reference
 
+// Lane state of a resumable traversal.  Encodings are chosen so that the two warp votes are single compares:
+//   can take a node step       <=>  cur >= 0
+//   can take a primitive step  <=>  leaf_left > 0
+// stack[0] always holds kTravDone, so a pop never needs an emptiness check.
 struct Trav {
-    int32_t cur;        // >= 0 inner node, < 0 leaf reference, kTravDone = nothing left to visit
-    int32_t leaf_next;  // next primitive of the postponed leaf (leaf-order position)
-    int32_t leaf_left;  // primitives of the postponed leaf still to test (0 = no leaf held)
+    int32_t cur;        // >= 0 inner node, < 0 leaf reference (blocked until the held leaf is done), kTravDone = exhausted
+    int32_t leaf_next;  // next primitive of the held leaf (leaf-order position)
+    int32_t leaf_left;  // primitives of the held leaf still to test (0 = no leaf held)
     int32_t sp;
     float3 inv, oinv;
     Hit best;
 };
 
-__device__ __forceinline__ void trav_begin(Trav &t, float3 o, float3 d) {
+__device__ __forceinline__ void trav_idle(Trav &t) {
+    t.cur = kTravDone;
+    t.leaf_left = 0;
+}
+__device__ __forceinline__ void trav_begin(Trav &t, int32_t *stack, float3 o, float3 d) {
     t.cur = 0;
     t.leaf_next = 0;
     t.leaf_left = 0;
-    t.sp = 0;
+    stack[0] = kTravDone;
+    t.sp = 1;
     t.inv = slab_inverse(d);
     t.oinv = f3(-o.x * t.inv.x, -o.y * t.inv.y, -o.z * t.inv.z);
     t.best.t = FLT_MAX;
     t.best.u = t.best.v = 0.f;
     t.best.prim = -1;
 }
-__device__ __forceinline__ bool trav_at_inner(const Trav &t) { return t.cur >= 0 && t.cur != kTravDone; }
-__device__ __forceinline__ bool trav_has_leaf(const Trav &t) { return t.leaf_left > 0; }
 __device__ __forceinline__ bool trav_finished(const Trav &t) { return t.cur == kTravDone && t.leaf_left == 0; }
-
-// moves a leaf reference sitting in `cur` into the postponed-leaf slot (if free) and pops the next node
-__device__ __forceinline__ void trav_postpone(Trav &t, const int32_t *stack) {
-    if (t.cur < 0 && t.leaf_left == 0) {
-        const int32_t v = ~t.cur;
-        t.leaf_next = v >> 3;
-        t.leaf_left = (v & 7) + 1;
-        t.cur = t.sp > 0 ? stack[--t.sp] : kTravDone;
-    }
+__device__ __forceinline__ void trav_hold_leaf(Trav &t, int32_t ref) {
+    const int32_t v = ~ref;
+    t.leaf_next = v >> 3;
+    t.leaf_left = (v & 7) + 1;
 }
 
-// one inner-node step (precondition: trav_at_inner)
+// one inner-node step (precondition: t.cur >= 0)
 template <bool COUNT>
 __device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, int32_t *stack, float tmin, uint32_t &n_box) {
     const float kSlack = 1.0000004f;
@@ -357,18 +359,30 @@ __device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, int3
     float rf = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), t.best.t));
     const bool hl = ln <= lf * kSlack;
     const bool hr = rn <= rf * kSlack;
-    const bool leftFirst = ln <= rn;
-    const int32_t nearRef = (hl & hr) ? (leftFirst ? refs.x : refs.y) : (hl ? refs.x : refs.y);
-    const int32_t farRef = leftFirst ? refs.y : refs.x;
-    if (hl & hr) stack[t.sp++] = farRef;
-    if (hl | hr) t.cur = nearRef;
-    else t.cur = t.sp > 0 ? stack[--t.sp] : kTravDone;
-    trav_postpone(t, stack);
+    const bool both = hl & hr;
+    const bool rightNear = hr & (!hl | (rn < ln));
+    int32_t next = rightNear ? refs.y : refs.x;
+    const int32_t other = rightNear ? refs.x : refs.y;
+    if (hl | hr) {
+        if (next < 0 && t.leaf_left == 0) {  // reached a leaf and the slot is free: hold it, keep descending elsewhere
+            trav_hold_leaf(t, next);
+            next = both ? other : stack[--t.sp];
+        } else if (both) {
+            stack[t.sp++] = other;
+        }
+    } else {
+        next = stack[--t.sp];
+    }
+    if (next < 0 && next != kTravDone && t.leaf_left == 0) {  // the popped entry is a leaf and the slot is free
+        trav_hold_leaf(t, next);
+        next = stack[--t.sp];
+    }
+    t.cur = next;
 }
 
-// one primitive of the postponed leaf (precondition: trav_has_leaf)
+// one primitive of the held leaf (precondition: t.leaf_left > 0)
 template <bool SPHERES, bool COUNT>
-__device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, const int32_t *stack, float3 o, float3 d, float tmin, uint32_t &n_tri) {
+__device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, int32_t *stack, float3 o, float3 d, float tmin, uint32_t &n_tri) {
     const int32_t k = t.leaf_next;
     const float4 q0 = __ldg(&sc.prims[k * 3 + 0]);
     const float4 q1 = __ldg(&sc.prims[k * 3 + 1]);
@@ -392,7 +406,10 @@ __device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, cons
     }
     t.leaf_next = k + 1;
     t.leaf_left -= 1;
-    if (t.leaf_left == 0) trav_postpone(t, stack);  // a second leaf may have been waiting in `cur`
+    if (t.leaf_left == 0 && t.cur < 0 && t.cur != kTravDone) {  // a second leaf was waiting in `cur`
+        trav_hold_leaf(t, t.cur);
+        t.cur = stack[--t.sp];
+    }
 }
 
 // ----------------------------------------------------------------------------------------

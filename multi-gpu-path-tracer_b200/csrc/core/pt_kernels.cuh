@@ -159,11 +159,12 @@ __global__ void __launch_bounds__(kBlockThreads) pt_persistent_kernel(const __gr
 // waiting the warp leaves TRAVERSE, shades exactly those lanes (they get their bounce ray or the next camera
 // ray) and re-enters with the unfinished lanes resuming where they stopped — warp-level ray compaction without
 // moving any state between lanes, which the one-XORWOW-stream-per-pixel contract forbids.
-template <bool SPHERES, bool RTOW, bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads) pt_wavefront_kernel(const __grid_constant__ RenderParams p) {
+template <bool SPHERES, bool RTOW, bool COUNT, int MINB>
+__global__ void __launch_bounds__(kBlockThreads, MINB) pt_wavefront_kernel(const __grid_constant__ RenderParams p) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t total_items = p.tiles.first_item[p.tiles.n];
     const int refill_at = p.refill_at;
+    const int node_burst = p.node_burst;
 
     bool retired = false, have_pixel = false, have_path = false;
     int px = 0, py = 0, pixel_index = 0;
@@ -173,10 +174,10 @@ __global__ void __launch_bounds__(kBlockThreads) pt_wavefront_kernel(const __gri
     float3 col = f3(0.f, 0.f, 0.f), att = f3(1.f, 1.f, 1.f), ro = f3(0.f, 0.f, 0.f), rd = f3(0.f, 0.f, 1.f);
     uint32_t n_rays = 0, n_box = 0, n_tri = 0, n_light = 0;
     unsigned long long acc_box = 0, acc_tri = 0, acc_light = 0;
-    Trav tr;
-    trav_begin(tr, ro, rd);
-    tr.cur = kTravDone;
     int32_t stack[kStackSize];
+    Trav tr;
+    trav_begin(tr, stack, ro, rd);
+    trav_idle(tr);
 
     for (;;) {
         // ---------------- GENERATE / COMPACT ----------------
@@ -212,28 +213,28 @@ __global__ void __launch_bounds__(kBlockThreads) pt_wavefront_kernel(const __gri
             camera_ray(p.cam, u, v, ro, rd);
             att = f3(1.0f, 1.0f, 1.0f);
             bounce = 0;
-            have_path = true;
-            trav_begin(tr, ro, rd);
-            n_rays++;
             if (p.depth == 0) {
-                have_path = false;
-                samples_done++;
-                n_rays--;
+                samples_done++;  // camera.h:52,82: the loop body never runs
+            } else {
+                have_path = true;
+                trav_begin(tr, stack, ro, rd);
+                n_rays++;
             }
         }
 
         // ---------------- TRAVERSE (warp-synchronous wavefront over uniform steps) ----------------
+        // lanes with a path are either still traversing (one of the two votes below is true) or finished and waiting
+        const int n_paths = __popc(__ballot_sync(kFullMask, have_path));
         for (;;) {
-            const bool work = have_path && !trav_finished(tr);
-            const bool can_node = work && trav_at_inner(tr);
-            const bool can_prim = work && trav_has_leaf(tr);
+            const bool can_node = tr.cur >= 0;
+            const bool can_prim = tr.leaf_left > 0;
             const unsigned m_node = __ballot_sync(kFullMask, can_node);
             const unsigned m_prim = __ballot_sync(kFullMask, can_prim);
-            if ((m_node | m_prim) == 0) break;
-            const unsigned m_wait = __ballot_sync(kFullMask, have_path && !work);
-            if (__popc(m_wait) >= refill_at) break;
+            const int n_active = __popc(m_node | m_prim);
+            if (n_active == 0 || n_paths - n_active >= refill_at) break;
             if (__popc(m_node) >= __popc(m_prim)) {
-                if (can_node) trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
+                for (int k = 0; k < node_burst; k++)
+                    if (tr.cur >= 0) trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
             } else {
                 if (can_prim) trav_prim_step<SPHERES, COUNT>(p.scene, tr, stack, ro, rd, 0.001f, n_tri);
             }
@@ -245,12 +246,13 @@ __global__ void __launch_bounds__(kBlockThreads) pt_wavefront_kernel(const __gri
             bool cont = shade<SPHERES, RTOW, COUNT>(p.scene, tr.best, ro, rd, att, rng, contrib, n_light);
             bounce++;
             if (cont && bounce < p.depth) {
-                trav_begin(tr, ro, rd);
+                trav_begin(tr, stack, ro, rd);
                 n_rays++;
             } else {
                 col = col + (cont ? f3(0.0f, 0.0f, 0.0f) : contrib);  // camera.h:82 exhausted -> (0,0,0)
                 have_path = false;
                 samples_done++;
+                trav_idle(tr);
             }
         }
         if (COUNT) {

@@ -68,6 +68,8 @@ struct ptcore {
     int blocks_per_sm = 0;
     int slice_spp = 0;
     int refill_at = 16;
+    int node_burst = 1;
+    int min_blocks = 6;
 
     PtStats build_stats{};
 };
@@ -146,7 +148,8 @@ cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaS
     } else {
         int occ = 0;
         cudaError_t e = h->kernel == PT_KERNEL_LOCKSTEP ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_persistent_kernel<S, R, C>, kBlockThreads, 0)
-                                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_wavefront_kernel<S, R, C>, kBlockThreads, 0);
+                        : h->min_blocks >= 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_wavefront_kernel<S, R, C, 8>, kBlockThreads, 0)
+                                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_wavefront_kernel<S, R, C, 6>, kBlockThreads, 0);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
         if (h->blocks_per_sm > 0) occ = std::min(occ, h->blocks_per_sm);
@@ -154,7 +157,8 @@ cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaS
         uint32_t needed = (total + kBlockThreads - 1) / kBlockThreads;
         if (grid > needed) grid = needed;
         if (h->kernel == PT_KERNEL_LOCKSTEP) pt_persistent_kernel<S, R, C><<<grid, kBlockThreads, 0, stream>>>(rp);
-        else pt_wavefront_kernel<S, R, C><<<grid, kBlockThreads, 0, stream>>>(rp);
+        else if (h->min_blocks >= 8) pt_wavefront_kernel<S, R, C, 8><<<grid, kBlockThreads, 0, stream>>>(rp);
+        else pt_wavefront_kernel<S, R, C, 6><<<grid, kBlockThreads, 0, stream>>>(rp);
     }
     return cudaGetLastError();
 }
@@ -204,7 +208,7 @@ int render_tiles(ptcore *h, const PtTile *tiles, int32_t n_tiles, cudaStream_t s
         rp.spp = h->spp;
         rp.depth = h->depth;
         rp.refill_at = h->refill_at;
-        rp.pad0 = 0;
+        rp.node_burst = h->node_burst;
         rp.fb_rgb = h->fb_rgb;
         rp.fb_yuv = h->fb_yuv;
         rp.counters = h->d_counters;
@@ -489,6 +493,14 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
         case PT_OPT_REFILL_AT:
             if (value < 1 || value > 32) return fail(h, PT_ERR_INVALID_ARGUMENT, "refill_at must be in [1, 32]");
             h->refill_at = (int)value;
+            return PT_OK;
+        case PT_OPT_NODE_BURST:
+            if (value < 1 || value > 4) return fail(h, PT_ERR_INVALID_ARGUMENT, "node_burst must be in [1, 4]");
+            h->node_burst = (int)value;
+            return PT_OK;
+        case PT_OPT_MIN_BLOCKS:
+            if (value != 6 && value != 8) return fail(h, PT_ERR_INVALID_ARGUMENT, "min_blocks must be 6 or 8");
+            h->min_blocks = (int)value;
             return PT_OK;
         case PT_OPT_SLICE_SPP:
             if (value != 0) return fail(h, PT_ERR_UNSUPPORTED, "sample slicing is not implemented yet");
