@@ -180,9 +180,6 @@ def main():
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--node-burst", type=int, default=0)
     ap.add_argument("--min-blocks", type=int, default=0)
-    ap.add_argument("--term-at", type=int, default=0)
-    ap.add_argument("--leaf-max", type=int, default=0)
-    ap.add_argument("--sah-isect", type=int, default=0, help="SAH primitive cost in 1/1000 of a node visit")
     ap.add_argument("--tile", default="64x32")
     ap.add_argument("--claim", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,10 +213,6 @@ def main():
     spp = args.spp
     scene = ptb200.load_scene_file(SCENE)
     pt = ptb200.PathTracer(local_rank)
-    if args.leaf_max:
-        pt.set_option(ptb200.PT_OPT_BVH_LEAF_MAX, args.leaf_max)
-    if args.sah_isect:
-        pt.set_option(ptb200.PT_OPT_SAH_ISECT_MILLI, args.sah_isect)
     pt.upload_scene(scene)
     pt.set_camera()
     pt.set_params(spp, DEPTH)
@@ -232,8 +225,6 @@ def main():
         pt.set_option(ptb200.PT_OPT_NODE_BURST, args.node_burst)
     if args.min_blocks:
         pt.set_option(ptb200.PT_OPT_MIN_BLOCKS, args.min_blocks)
-    if args.term_at:
-        pt.set_option(ptb200.PT_OPT_TERM_AT, args.term_at)
 
     tw, th = (int(x) for x in args.tile.split("x"))
     if world == 1:

@@ -105,9 +105,7 @@ enum { /* ptcore_set_option keys */
     PT_OPT_SLICE_SPP = 5,    /* samples a lane runs on one pixel before handing it back to the pool (0 = whole pixel) */
     PT_OPT_REFILL_AT = 6,    /* wavefront kernel: finished lanes per warp that trigger a shade/refill pass (1..32, default 16) */
     PT_OPT_NODE_BURST = 7,   /* wavefront kernel: node steps per warp vote (1..4) */
-    PT_OPT_MIN_BLOCKS = 8,   /* wavefront kernel build: __launch_bounds__(128, 6) (80 registers) or (128, 8) (64 registers) */
-    PT_OPT_SAH_ISECT_MILLI = 9,/* SAH primitive-test cost relative to a node visit, in 1/1000 (default 1200), for the next upload */
-    PT_OPT_TERM_AT = 10      /* wavefront kernel: lanes waiting for a TERMINATE/GENERATE step that trigger one (1..32, default 8) */
+    PT_OPT_MIN_BLOCKS = 8    /* wavefront kernel build: __launch_bounds__(128, 6) (80 registers) or (128, 8) (64 registers) */
 };
 enum {
     PT_KERNEL_PERSISTENT = 0, /* persistent-thread wavefront: per-lane pixel refill + warp-voted uniform traversal steps (default) */

@@ -62,10 +62,8 @@ struct RenderParams {
     DevScene scene;
     CamParams cam;
     uint32_t width, height, spp, depth;
-    int32_t refill_at;   // wavefront kernel: lanes waiting for a SHADE step that trigger one (1..32)
+    int32_t refill_at;   // wavefront kernel: finished lanes per warp that trigger a shade/refill pass (1..32)
     int32_t node_burst;  // wavefront kernel: node steps taken per vote (1..4)
-    int32_t term_at;     // wavefront kernel: lanes waiting for a TERMINATE/GENERATE step that trigger one (1..32)
-    int32_t pad1;
     uint8_t *fb_rgb, *fb_yuv;
     uint32_t *work_counter;
     DevCounters *counters;
@@ -324,7 +322,6 @@ struct Trav {
     int32_t sp;
     float3 inv, oinv;
     Hit best;
-    int32_t best_flags;  // flags word of the closest primitive so far (bit 0: hit ends the path with a constant emission)
 };
 
 __device__ __forceinline__ void trav_idle(Trav &t) {
@@ -342,7 +339,6 @@ __device__ __forceinline__ void trav_begin(Trav &t, int32_t *stack, float3 o, fl
     t.best.t = FLT_MAX;
     t.best.u = t.best.v = 0.f;
     t.best.prim = -1;
-    t.best_flags = 0;
 }
 __device__ __forceinline__ bool trav_finished(const Trav &t) { return t.cur == kTravDone && t.leaf_left == 0; }
 __device__ __forceinline__ void trav_hold_leaf(Trav &t, int32_t ref) {
@@ -408,7 +404,6 @@ __device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, int3
             t.best.t = tt;
             t.best.u = t.best.v = 0.f;
             t.best.prim = k;
-            t.best_flags = __float_as_int(q2.w);
         }
     } else {
         float tt, u, w;
@@ -417,7 +412,6 @@ __device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, int3
             t.best.u = u;
             t.best.v = w;
             t.best.prim = k;
-            t.best_flags = __float_as_int(q2.w);
         }
     }
     t.leaf_next = k + 1;
@@ -543,19 +537,6 @@ __device__ __forceinline__ void store_pixel(const RenderParams &p, int pixel_ind
             if (totalPixels + uvSize + uvIndex < limit) p.fb_yuv[totalPixels + uvSize + uvIndex] = (uint8_t)(((112 * r - 94 * g - 18 * b + 128) >> 8) + 128);
         }
     }
-}
-
-// Contribution of a path that ended on a miss or on a primitive flagged "constant emitter" (prim flags bit 0):
-// exactly what shade() computes for those cases (camera.h:72-79,109; material.h:80-86 without an emissive texture),
-// split out so that such lanes can be retired by the cheap TERMINATE/GENERATE step instead of waiting for a SHADE step.
-template <bool RTOW>
-__device__ __forceinline__ float3 terminal_contribution(const DevScene &sc, const Hit &h, float3 att) {
-    if (h.prim < 0) return f3(0.0f, 0.0f, 0.0f) * att;
-    const int mat = __float_as_int(__ldg(&sc.shade[h.prim * 2 + 1]).z);
-    const float4 m1 = __ldg(&sc.mats[mat * 3 + 1]);
-    const float3 emis = f3(m1.x, m1.y, m1.z);
-    if (RTOW && __float_as_int(__ldg(&sc.mats[mat * 3 + 0]).x) == 3 /* DIFFUSE_LIGHT */) return att * emis;
-    return att * (emis * 50);
 }
 
 // ----------------------------------------------------------------------------------------

@@ -149,30 +149,22 @@ __global__ void __launch_bounds__(kBlockThreads) pt_persistent_kernel(const __gr
     }
 }
 
-// pt_wavefront_kernel — the default.  A persistent-thread wavefront over FOUR kinds of uniform steps, chosen by warp
-// votes; every lane owns one pixel's XORWOW stream (the reference's "one curandState per pixel, samples in sequence"
-// contract) and is always in exactly one of these states:
-//
-//   NODE      at an inner BVH node                      -> trav_node_step   (two slab tests, push/pop, hold a leaf)
-//   PRIM      holds a leaf primitive                     -> trav_prim_step   (one Moeller-Trumbore / sphere test)
-//   TERM/GEN  ray finished on a miss or a constant emitter, or the lane has no path
-//                                                        -> add the contribution, store a finished pixel, fetch the next
-//                                                           pixel (warp-aggregated atomic), generate the next camera ray
-//   SHADE     ray finished on a scattering surface        -> shade(): material, light/cosine sampling, pdfs, next ray
-//
-// Each iteration the warp runs ONE kind of step for all lanes in that state:
-//   TERM/GEN when >= term_at lanes wait for it, SHADE when >= refill_at lanes wait for it (or when nothing can traverse),
-//   otherwise NODE if at least as many lanes are at a node as hold a primitive, else PRIM.
-// So box tests, triangle tests and shading each run with a large part of the warp instead of whatever lanes happen to
-// agree (ncu, per-lane traversal loop: 7.0 threads per executed instruction, 3.2 inside the triangle test:
-// profiles/r01_ncu_persistent_lockstep.txt), finished lanes are replaced without moving state between lanes
-// (warp-level ray compaction), and the cheap path endings (40 % of all ray ends on cornell_duck) do not wait for the
-// expensive SHADE step.
+// pt_wavefront_kernel — the default.  Same per-lane pixel ownership and refill as pt_persistent_kernel, but the
+// TRAVERSE stage is a warp-synchronous wavefront over uniform steps (pt_device.cuh: trav_node_step /
+// trav_prim_step): every iteration the warp votes and executes ONE kind of step for all lanes that can take it,
+//       #lanes at an inner node  >=  #lanes holding a leaf primitive   ->  node step      else  primitive step,
+// so box tests and Moeller-Trumbore tests each run with most of the warp instead of a handful of lanes
+// (ncu on pt_persistent_kernel: 7.0 threads per executed instruction, 3.2 inside the triangle test;
+// profiles/r01_ncu_persistent_lockstep.txt).  Lanes whose ray is finished wait; once `refill_at` of them are
+// waiting the warp leaves TRAVERSE, shades exactly those lanes (they get their bounce ray or the next camera
+// ray) and re-enters with the unfinished lanes resuming where they stopped — warp-level ray compaction without
+// moving any state between lanes, which the one-XORWOW-stream-per-pixel contract forbids.
 template <bool SPHERES, bool RTOW, bool COUNT, int MINB>
 __global__ void __launch_bounds__(kBlockThreads, MINB) pt_wavefront_kernel(const __grid_constant__ RenderParams p) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t total_items = p.tiles.first_item[p.tiles.n];
-    const int shade_at = p.refill_at, term_at = p.term_at, node_burst = p.node_burst;
+    const int refill_at = p.refill_at;
+    const int node_burst = p.node_burst;
 
     bool retired = false, have_pixel = false, have_path = false;
     int px = 0, py = 0, pixel_index = 0;
@@ -187,99 +179,81 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) pt_wavefront_kernel(const
     trav_begin(tr, stack, ro, rd);
     trav_idle(tr);
 
-    int prev_trav = -1, n_tg = 0, n_sh = 0;
     for (;;) {
-        const bool can_node = tr.cur >= 0;
-        const bool can_prim = tr.leaf_left > 0;
-        const unsigned m_node = __ballot_sync(kFullMask, can_node);
-        const unsigned m_prim = __ballot_sync(kFullMask, can_prim);
-        const int n_trav = __popc(m_node | m_prim);
-        const bool fin = have_path && !can_node && !can_prim;
-        const bool want_term = fin && (tr.best.prim < 0 || (tr.best_flags & 1));
-        const bool want_shade = fin && !want_term;
-        const bool want_gen = !have_path && !retired;
-        if (n_trav != prev_trav) {  // somebody finished (or new rays started): recount the waiting lanes
-            n_tg = __popc(__ballot_sync(kFullMask, want_term || want_gen));
-            n_sh = __popc(__ballot_sync(kFullMask, want_shade));
-            prev_trav = n_trav;
+        // ---------------- GENERATE / COMPACT ----------------
+        if (!have_path && have_pixel && samples_done == p.spp) {
+            store_pixel(p, pixel_index, col);
+            have_pixel = false;
+        }
+        const bool need = !retired && !have_pixel;
+        const unsigned need_mask = __ballot_sync(kFullMask, need);
+        if (need_mask) {
+            const int leader = __ffs((int)need_mask) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(p.work_counter, (uint32_t)__popc(need_mask));
+            base = __shfl_sync(kFullMask, base, leader);
+            if (need) {
+                const uint32_t item = base + (uint32_t)__popc(need_mask & ((1u << lane) - 1u));
+                if (item >= total_items) {
+                    retired = true;
+                } else if (item_to_pixel(p.tiles, item, px, py)) {
+                    pixel_index = ((int)p.height - py - 1) * (int)p.width + px;
+                    rng_init(rng, (unsigned long long)(long long)(1984 + pixel_index));
+                    col = f3(0.f, 0.f, 0.f);
+                    samples_done = 0;
+                    have_pixel = true;
+                }
+            }
+        }
+        if (__all_sync(kFullMask, retired)) break;
+
+        if (!have_path && have_pixel && samples_done < p.spp) {
+            float u = float(px + rng_uniform(rng)) / float(p.width);
+            float v = float(py + rng_uniform(rng)) / float(p.height);
+            camera_ray(p.cam, u, v, ro, rd);
+            att = f3(1.0f, 1.0f, 1.0f);
+            bounce = 0;
+            if (p.depth == 0) {
+                samples_done++;  // camera.h:52,82: the loop body never runs
+            } else {
+                have_path = true;
+                trav_begin(tr, stack, ro, rd);
+                n_rays++;
+            }
         }
 
-        if (n_tg > 0 && (n_tg >= term_at || n_trav == 0)) {
-            // ---------------- TERMINATE / GENERATE / COMPACT ----------------
-            if (want_term) {
-                col = col + terminal_contribution<RTOW>(p.scene, tr.best, att);  // DevicePathTracer.h:87
-                have_path = false;
-                samples_done++;
-                trav_idle(tr);
-            }
-            if (!have_path && have_pixel && samples_done == p.spp) {
-                store_pixel(p, pixel_index, col);
-                have_pixel = false;
-            }
-            const bool need = !retired && !have_pixel;
-            const unsigned need_mask = __ballot_sync(kFullMask, need);
-            if (need_mask) {
-                const int leader = __ffs((int)need_mask) - 1;
-                uint32_t base = 0;
-                if ((int)lane == leader) base = atomicAdd(p.work_counter, (uint32_t)__popc(need_mask));
-                base = __shfl_sync(kFullMask, base, leader);
-                if (need) {
-                    const uint32_t item = base + (uint32_t)__popc(need_mask & ((1u << lane) - 1u));
-                    if (item >= total_items) {
-                        retired = true;
-                    } else if (item_to_pixel(p.tiles, item, px, py)) {
-                        // DevicePathTracer.h:79: framebuffer row 0 is the top image row; :54: seed = 1984 + pixel_index
-                        pixel_index = ((int)p.height - py - 1) * (int)p.width + px;
-                        rng_init(rng, (unsigned long long)(long long)(1984 + pixel_index));
-                        col = f3(0.f, 0.f, 0.f);
-                        samples_done = 0;
-                        have_pixel = true;
-                    }
-                }
-            }
-            if (!have_path && have_pixel && samples_done < p.spp) {
-                // DevicePathTracer.h:84-87
-                float u = float(px + rng_uniform(rng)) / float(p.width);
-                float v = float(py + rng_uniform(rng)) / float(p.height);
-                camera_ray(p.cam, u, v, ro, rd);
-                att = f3(1.0f, 1.0f, 1.0f);
-                bounce = 0;
-                if (p.depth == 0) {
-                    samples_done++;  // camera.h:52,82: the bounce loop never runs, the sample adds (0,0,0)
-                } else {
-                    have_path = true;
-                    trav_begin(tr, stack, ro, rd);
-                    n_rays++;
-                }
-            }
-            prev_trav = -1;
-        } else if (n_sh > 0 && (n_sh >= shade_at || n_trav == 0)) {
-            // ---------------- SHADE ----------------
-            if (want_shade) {
-                float3 contrib;
-                const bool cont = shade<SPHERES, RTOW, COUNT>(p.scene, tr.best, ro, rd, att, rng, contrib, n_light);
-                bounce++;
-                if (cont && bounce < p.depth) {
-                    trav_begin(tr, stack, ro, rd);
-                    n_rays++;
-                } else {
-                    col = col + (cont ? f3(0.0f, 0.0f, 0.0f) : contrib);  // camera.h:82: exhausted -> (0,0,0)
-                    have_path = false;
-                    samples_done++;
-                    trav_idle(tr);
-                }
-            }
-            prev_trav = -1;
-        } else if (n_trav > 0) {
-            // ---------------- TRAVERSE ----------------
+        // ---------------- TRAVERSE (warp-synchronous wavefront over uniform steps) ----------------
+        // lanes with a path are either still traversing (one of the two votes below is true) or finished and waiting
+        const int n_paths = __popc(__ballot_sync(kFullMask, have_path));
+        for (;;) {
+            const bool can_node = tr.cur >= 0;
+            const bool can_prim = tr.leaf_left > 0;
+            const unsigned m_node = __ballot_sync(kFullMask, can_node);
+            const unsigned m_prim = __ballot_sync(kFullMask, can_prim);
+            const int n_active = __popc(m_node | m_prim);
+            if (n_active == 0 || n_paths - n_active >= refill_at) break;
             if (__popc(m_node) >= __popc(m_prim)) {
                 for (int k = 0; k < node_burst; k++)
                     if (tr.cur >= 0) trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
             } else {
                 if (can_prim) trav_prim_step<SPHERES, COUNT>(p.scene, tr, stack, ro, rd, 0.001f, n_tri);
             }
-        } else {
-            break;  // nothing traverses, nothing waits: every lane is retired
+        }
+
+        // ---------------- SHADE (only lanes whose ray is finished) ----------------
+        if (have_path && trav_finished(tr)) {
+            float3 contrib;
+            bool cont = shade<SPHERES, RTOW, COUNT>(p.scene, tr.best, ro, rd, att, rng, contrib, n_light);
+            bounce++;
+            if (cont && bounce < p.depth) {
+                trav_begin(tr, stack, ro, rd);
+                n_rays++;
+            } else {
+                col = col + (cont ? f3(0.0f, 0.0f, 0.0f) : contrib);  // camera.h:82 exhausted -> (0,0,0)
+                have_path = false;
+                samples_done++;
+                trav_idle(tr);
+            }
         }
         if (COUNT) {
             acc_box += n_box; acc_tri += n_tri; acc_light += n_light;

@@ -67,11 +67,9 @@ struct ptcore {
     int leaf_max = 4;
     int blocks_per_sm = 0;
     int slice_spp = 0;
-    int refill_at = 16;
-    int node_burst = 1;
-    int min_blocks = 6;
-    int sah_isect_milli = 1200;
-    int term_at = 8;
+    int refill_at = 24;
+    int node_burst = 2;
+    int min_blocks = 8;
 
     PtStats build_stats{};
 };
@@ -98,15 +96,6 @@ inline float as_float(int32_t i) {
     float f;
     memcpy(&f, &i, 4);
     return f;
-}
-
-// bit 0 of a primitive's flags word: a hit on it ends the path with a constant emission (no texture lookup, no
-// scattering), i.e. exactly the cases shade() leaves through its emitter exits (material.h:62-65,80-86; :210-217)
-int32_t terminal_flag(const PtMaterial &m) {
-    if (m.type == PT_MAT_DIFFUSE_LIGHT) return 1;
-    if (m.type != PT_MAT_UNIVERSAL || m.emis_tex >= 0) return 0;
-    const float e0 = m.emis[0] * 50, e1 = m.emis[1] * 50, e2 = m.emis[2] * 50;
-    return (e0 > 0.0001f || e1 > 0.0001f || e2 > 0.0001f) ? 1 : 0;
 }
 
 // triangle.h:28 — evaluated on the host by the reference as well (the triangle constructor is host code)
@@ -220,8 +209,6 @@ int render_tiles(ptcore *h, const PtTile *tiles, int32_t n_tiles, cudaStream_t s
         rp.depth = h->depth;
         rp.refill_at = h->refill_at;
         rp.node_burst = h->node_burst;
-        rp.term_at = h->term_at;
-        rp.pad1 = 0;
         rp.fb_rgb = h->fb_rgb;
         rp.fb_yuv = h->fb_yuv;
         rp.counters = h->d_counters;
@@ -326,7 +313,6 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
 
     BvhBuildOptions opt;
     opt.leaf_max = h->leaf_max;
-    opt.intersect_cost = (float)h->sah_isect_milli / 1000.f;
     BvhBuildResult bvh = build_bvh(pb, opt);
 
     // ---- lights: DevicePathTracer.h:302-307 (emissiveFactor channel > 0.0001, scene order) ----
@@ -370,7 +356,7 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
             q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
             q[3] = p[3] - p[0]; q[4] = p[4] - p[1]; q[5] = p[5] - p[2];  // e1 = v1 - v0, triangle.h:67
             q[6] = p[6] - p[0]; q[7] = p[7] - p[1]; q[8] = p[8] - p[2];  // e2 = v2 - v0, triangle.h:68
-            q[9] = 0.f; q[10] = as_float(0); q[11] = as_float(terminal_flag(sc->mats[sc->tri_mat[id]]));
+            q[9] = 0.f; q[10] = as_float(0); q[11] = 0.f;
             if (sc->tri_uv) memcpy(s, sc->tri_uv + (size_t)id * 6, 6 * sizeof(float));
             s[6] = as_float(sc->tri_mat[id]);
         } else {
@@ -378,7 +364,6 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
             const float *sp = sc->sph + (size_t)si * 4;
             q[0] = sp[0]; q[1] = sp[1]; q[2] = sp[2]; q[3] = sp[3];
             q[10] = as_float(1);
-            q[11] = as_float(terminal_flag(sc->mats[sc->sph_mat[si]]));
             s[6] = as_float(sc->sph_mat[si]);
             nb.has_spheres = true;
         }
@@ -516,14 +501,6 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
         case PT_OPT_MIN_BLOCKS:
             if (value != 6 && value != 8) return fail(h, PT_ERR_INVALID_ARGUMENT, "min_blocks must be 6 or 8");
             h->min_blocks = (int)value;
-            return PT_OK;
-        case PT_OPT_SAH_ISECT_MILLI:
-            if (value < 1 || value > 100000) return fail(h, PT_ERR_INVALID_ARGUMENT, "sah_isect_milli out of range");
-            h->sah_isect_milli = (int)value;
-            return PT_OK;
-        case PT_OPT_TERM_AT:
-            if (value < 1 || value > 32) return fail(h, PT_ERR_INVALID_ARGUMENT, "term_at must be in [1, 32]");
-            h->term_at = (int)value;
             return PT_OK;
         case PT_OPT_SLICE_SPP:
             if (value != 0) return fail(h, PT_ERR_UNSUPPORTED, "sample slicing is not implemented yet");

@@ -143,9 +143,8 @@ def test_direct_kernel_equals_persistent_kernel(tracer, duck, ptb):
     c, yc = render(tracer, duck, 120, 68, 6, 6, kernel=ptb.PT_KERNEL_LOCKSTEP, ptb=ptb)
     assert np.array_equal(a, c) and np.array_equal(ya, yc)
     # the step-scheduling knobs only change WHEN lanes run which step, never pixels
-    for refill_at, term_at, burst, minb in ((1, 1, 1, 6), (5, 32, 3, 8), (32, 3, 2, 6), (20, 8, 4, 8)):
+    for refill_at, burst, minb in ((1, 1, 6), (5, 3, 8), (32, 2, 6), (20, 4, 8)):
         tracer.set_option(ptb.PT_OPT_REFILL_AT, refill_at)
-        tracer.set_option(ptb.PT_OPT_TERM_AT, term_at)
         tracer.set_option(ptb.PT_OPT_NODE_BURST, burst)
         tracer.set_option(ptb.PT_OPT_MIN_BLOCKS, minb)
         d, yd = render(tracer, duck, 120, 68, 6, 6, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
