@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--node-burst", type=int, default=0)
     ap.add_argument("--min-blocks", type=int, default=0)
+    ap.add_argument("--sched", default="lpt", choices=["lpt", "tiles"], help="lpt: pilot pass + cost-sorted 8x4 blocks dealt round-robin to the ranks; tiles: dynamic tile claims")
+    ap.add_argument("--pilot-spp", type=int, default=4)
     ap.add_argument("--tile", default="64x32")
     ap.add_argument("--claim", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -253,6 +255,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    def render_frame():
+        if args.sched == "lpt" and args.kernel == "persistent":
+            rr.render_frame_lpt(rank, world, args.pilot_spp)
+        else:
+            rr.render_frame(plan, queue, rank, world)
+
     def step():
         """one frame; returns device milliseconds (CUDA events on the launching stream)"""
         flush.zero_()
@@ -263,7 +271,7 @@ def main():
             barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        rr.render_frame(plan, queue, rank, world)
+        render_frame()
         e1.record()
         e1.synchronize()
         return e0.elapsed_time(e1)
@@ -330,7 +338,7 @@ def main():
                 pt.render_frame_host(WIDTH, HEIGHT, True, rgb_np, yuv_np)
                 d2h = rgb_np.nbytes + yuv_np.nbytes
             else:
-                rr.render_frame(plan, queue, rank, world)
+                render_frame()
                 if rank == 0:
                     rgb_host.view(-1).copy_(rr.rgb, non_blocking=True)
                     yuv_host.copy_(rr.yuv, non_blocking=True)
@@ -354,8 +362,8 @@ def main():
     if rank == 0:
         peaks = measured_peaks()
         n_kernel_launches = max(1, launches)
-        kernel_ms = total_ms / (n_kernel_launches if world == 1 else args.steps)  # N=1: one launch per step
-        rays_per_launch = rays / (n_kernel_launches if world == 1 else args.steps * world)
+        kernel_ms = total_ms / args.steps                 # the dominant launch (one per rank and step) spans the step
+        rays_per_launch = rays / (args.steps * world)      # per GPU
         abytes = BYTES_PER_RAY(per_ray["box"], per_ray["tri"]) * rays_per_launch
         aflops = FLOPS_PER_RAY(per_ray["box"], per_ray["tri"]) * rays_per_launch
         sm_mhz = (clocks or {}).get("sm_mhz") or peaks["sm_max_mhz"]
@@ -371,7 +379,7 @@ def main():
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "reference model cornell_duck (converted fixture), fixed XORWOW seeds",
                 "config": {"workload": WORKLOAD if spp == SPP else WORKLOAD + f" [spp overridden to {spp}]", "kernel": args.kernel, "l2": "flushed between steps (256 MiB write)",
-                           "parallelism": "1 GPU" if world == 1 else f"image tiles {tw}x{th}, dynamic claims of {claim}, NCCL reduce gather",
+                           "parallelism": ("1 GPU" if world == 1 else f"{world} ranks") + (f", pilot pass ({args.pilot_spp} spp) + cost-sorted 8x4 blocks dealt round-robin (LPT), NCCL reduce gather" if args.sched == "lpt" and args.kernel == "persistent" else f", image tiles {tw}x{th}, dynamic claims of {claim}, NCCL reduce gather"),
                            "rng": "XORWOW per pixel, reference stream order"},
                 "mrays_per_s": mrays, "rays_per_sample": rays / (samples_per_step * args.steps), "per_ray": per_ray, "wall_s_timed_region": t_wall,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_fp32": roofline_fp32}

@@ -155,6 +155,13 @@ int ptcore_bind_framebuffer(ptcore_t *h, uint8_t *rgb, uint8_t *yuv, uint32_t wi
 /* ---- render (renderTaskAsync :194-214 / synchronizeStream :222-226 / waitForRenderTask :216-220) ---- */
 int ptcore_render_tile_async(ptcore_t *h, int32_t offset_x, int32_t offset_y, int32_t width, int32_t height, void *stream);
 int ptcore_render_tiles_async(ptcore_t *h, const PtTile *tiles, int32_t n_tiles, void *stream);
+/* Explicit work list: 8x4-pixel blocks, blocks[i] = bx | (by << 16) with block origin (8*bx, 4*by) in the same bottom-up
+ * pixel space as RenderTask.  `blocks_dev` is a DEVICE pointer that must stay valid until the launch has finished.  Lanes take
+ * blocks in list order, so a list sorted by descending cost gives longest-processing-time-first scheduling. */
+int ptcore_render_blocks_async(ptcore_t *h, const uint32_t *blocks_dev, uint32_t n_blocks, void *stream);
+/* Pilot pass: traces `pilot_spp` samples of every pixel (same RNG streams, nothing is stored) and accumulates the number of
+ * rays per 8x4 block into costs_dev[by * ceil(W/8) + bx] (DEVICE uint32 array, zeroed by the call). */
+int ptcore_block_costs_async(ptcore_t *h, uint32_t pilot_spp, uint32_t *costs_dev, void *stream);
 int ptcore_sync(ptcore_t *h, void *stream);
 int ptcore_wait(ptcore_t *h);
 

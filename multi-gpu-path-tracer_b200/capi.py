@@ -194,6 +194,8 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         "ptcore_bind_framebuffer": (C.c_int, [vp, vp, vp, u32, u32]),
         "ptcore_render_tile_async": (C.c_int, [vp, i32, i32, i32, i32, vp]),
         "ptcore_render_tiles_async": (C.c_int, [vp, C.POINTER(PtTile), i32, vp]),
+        "ptcore_render_blocks_async": (C.c_int, [vp, vp, u32, vp]),
+        "ptcore_block_costs_async": (C.c_int, [vp, u32, vp, vp]),
         "ptcore_sync": (C.c_int, [vp, vp]),
         "ptcore_wait": (C.c_int, [vp]),
         "ptcore_render_frame_host": (C.c_int, [vp, u32, u32, vp, vp]),
@@ -326,6 +328,14 @@ class PathTracer:
         for i, (ox, oy, w, h) in enumerate(tiles):
             arr[i] = PtTile(w, h, ox, oy)
         self._ck(self.lib.ptcore_render_tiles_async(self.h, arr, len(tiles), stream or None))
+
+    def render_blocks_async(self, blocks_dev_ptr: int, n_blocks: int, stream: int = 0) -> None:
+        """blocks: DEVICE uint32 array, entry = bx | (by << 16) of an 8x4-pixel block; lanes take them in list order."""
+        self._ck(self.lib.ptcore_render_blocks_async(self.h, blocks_dev_ptr, n_blocks, stream or None))
+
+    def block_costs_async(self, pilot_spp: int, costs_dev_ptr: int, stream: int = 0) -> None:
+        """Pilot pass: rays per 8x4 block over pilot_spp samples into a DEVICE uint32[ceil(W/8)*ceil(H/4)] array."""
+        self._ck(self.lib.ptcore_block_costs_async(self.h, pilot_spp, costs_dev_ptr, stream or None))
 
     def sync(self, stream: int = 0) -> None:
         self._ck(self.lib.ptcore_sync(self.h, stream or None))

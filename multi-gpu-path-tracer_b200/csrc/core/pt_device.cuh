@@ -67,6 +67,12 @@ struct RenderParams {
     uint8_t *fb_rgb, *fb_yuv;
     uint32_t *work_counter;
     DevCounters *counters;
+    // explicit work list (ptcore_render_blocks_async): 8x4-pixel blocks, block_list[i] = bx | (by << 16); NULL = use `tiles`
+    const uint32_t *block_list;
+    uint32_t n_blocks;
+    uint32_t pad2;
+    // pilot pass (ptcore_block_costs_async): rays traced per 8x4 block are accumulated here and no pixel is stored
+    uint32_t *block_cost;
     TileList tiles;
 };
 

@@ -39,6 +39,23 @@ __device__ __forceinline__ bool item_to_pixel(const TileList &tl, uint32_t item,
     return lx < tl.w[t] && ly < tl.h[t];
 }
 
+// work item -> pixel for either kind of work list
+__device__ __forceinline__ uint32_t work_total(const RenderParams &p) { return p.block_list ? p.n_blocks * 32u : p.tiles.first_item[p.tiles.n]; }
+__device__ __forceinline__ bool work_to_pixel(const RenderParams &p, uint32_t item, int &x, int &y) {
+    if (p.block_list) {
+        const uint32_t b = __ldg(&p.block_list[item >> 5]), within = item & 31u;
+        x = (int)((b & 0xffffu) * 8u + (within & 7u));
+        y = (int)((b >> 16) * 4u + (within >> 3));
+        return x < (int)p.width && y < (int)p.height;
+    }
+    return item_to_pixel(p.tiles, item, x, y);
+}
+// a finished pixel: normally the quantised store; in the pilot pass its ray count goes to the block-cost map instead
+__device__ __forceinline__ void finish_pixel(const RenderParams &p, int px, int py, int pixel_index, float3 col, uint32_t pixel_rays) {
+    if (p.block_cost) atomicAdd(&p.block_cost[(uint32_t)(py >> 2) * ((p.width + 7u) >> 3) + (uint32_t)(px >> 3)], pixel_rays);
+    else store_pixel(p, pixel_index, col);
+}
+
 template <bool SPHERES, bool RTOW, bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads) pt_persistent_kernel(const __grid_constant__ RenderParams p) {
     const unsigned lane = threadIdx.x & 31u;
@@ -162,7 +179,7 @@ __global__ void __launch_bounds__(kBlockThreads) pt_persistent_kernel(const __gr
 template <bool SPHERES, bool RTOW, bool COUNT, int MINB>
 __global__ void __launch_bounds__(kBlockThreads, MINB) pt_wavefront_kernel(const __grid_constant__ RenderParams p) {
     const unsigned lane = threadIdx.x & 31u;
-    const uint32_t total_items = p.tiles.first_item[p.tiles.n];
+    const uint32_t total_items = work_total(p);
     const int refill_at = p.refill_at;
     const int node_burst = p.node_burst;
 
@@ -172,7 +189,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) pt_wavefront_kernel(const
     Rng rng;
     rng_init(rng, 0);
     float3 col = f3(0.f, 0.f, 0.f), att = f3(1.f, 1.f, 1.f), ro = f3(0.f, 0.f, 0.f), rd = f3(0.f, 0.f, 1.f);
-    uint32_t n_rays = 0, n_box = 0, n_tri = 0, n_light = 0;
+    uint32_t n_rays = 0, n_box = 0, n_tri = 0, n_light = 0, pixel_rays = 0;
     unsigned long long acc_box = 0, acc_tri = 0, acc_light = 0;
     int32_t stack[kStackSize];
     Trav tr;
@@ -182,7 +199,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) pt_wavefront_kernel(const
     for (;;) {
         // ---------------- GENERATE / COMPACT ----------------
         if (!have_path && have_pixel && samples_done == p.spp) {
-            store_pixel(p, pixel_index, col);
+            finish_pixel(p, px, py, pixel_index, col, pixel_rays);
             have_pixel = false;
         }
         const bool need = !retired && !have_pixel;
@@ -196,11 +213,12 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) pt_wavefront_kernel(const
                 const uint32_t item = base + (uint32_t)__popc(need_mask & ((1u << lane) - 1u));
                 if (item >= total_items) {
                     retired = true;
-                } else if (item_to_pixel(p.tiles, item, px, py)) {
+                } else if (work_to_pixel(p, item, px, py)) {
                     pixel_index = ((int)p.height - py - 1) * (int)p.width + px;
                     rng_init(rng, (unsigned long long)(long long)(1984 + pixel_index));
                     col = f3(0.f, 0.f, 0.f);
                     samples_done = 0;
+                    pixel_rays = 0;
                     have_pixel = true;
                 }
             }
@@ -219,6 +237,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) pt_wavefront_kernel(const
                 have_path = true;
                 trav_begin(tr, stack, ro, rd);
                 n_rays++;
+                pixel_rays++;
             }
         }
 
@@ -248,6 +267,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) pt_wavefront_kernel(const
             if (cont && bounce < p.depth) {
                 trav_begin(tr, stack, ro, rd);
                 n_rays++;
+                pixel_rays++;
             } else {
                 col = col + (cont ? f3(0.0f, 0.0f, 0.0f) : contrib);  // camera.h:82 exhausted -> (0,0,0)
                 have_path = false;

@@ -70,6 +70,8 @@ struct ptcore {
     int refill_at = 24;
     int node_burst = 2;
     int min_blocks = 8;
+    uint32_t *ident_blocks = nullptr;
+    uint32_t ident_blocks_n = 0;
 
     PtStats build_stats{};
 };
@@ -193,6 +195,42 @@ void fill_dev_scene(ptcore *h) {
     d.pad = 0;
 }
 
+int render_blocks(ptcore *h, const uint32_t *blocks_dev, uint32_t n_blocks, uint32_t spp, uint32_t *block_cost, cudaStream_t stream) {
+    if (!h->have_scene) return fail(h, PT_ERR_NO_SCENE, "no scene uploaded");
+    if (!h->fb_rgb) return fail(h, PT_ERR_NO_FRAMEBUFFER, "no framebuffer bound");
+    if (!h->have_cam) return fail(h, PT_ERR_INVALID_ARGUMENT, "no camera set");
+    if (h->kernel != PT_KERNEL_PERSISTENT) return fail(h, PT_ERR_UNSUPPORTED, "block lists need the default (wavefront) kernel");
+    if (n_blocks == 0) return PT_OK;
+    if (n_blocks > 0x07ffffffu) return fail(h, PT_ERR_UNSUPPORTED, "too many blocks");
+    PT_CUDA(h, cudaSetDevice(h->device));
+    RenderParams rp;
+    memset(&rp, 0, sizeof rp);
+    rp.scene = h->dscene;
+    rp.cam = h->cam;
+    rp.width = h->fb_w;
+    rp.height = h->fb_h;
+    rp.spp = spp;
+    rp.depth = h->depth;
+    rp.refill_at = h->refill_at;
+    rp.node_burst = h->node_burst;
+    rp.fb_rgb = h->fb_rgb;
+    rp.fb_yuv = h->fb_yuv;
+    rp.counters = h->d_counters;
+    rp.block_list = blocks_dev;
+    rp.n_blocks = n_blocks;
+    rp.block_cost = block_cost;
+    rp.tiles.n = 1;  // work_total() reads the block list; keep the tile list well-formed for the launch-size computation
+    rp.tiles.first_item[0] = 0;
+    rp.tiles.first_item[1] = n_blocks * 32u;
+    uint64_t seq = h->launch_seq.fetch_add(1);
+    rp.work_counter = h->d_work + (seq % kCounterRing);
+    PT_CUDA(h, cudaMemsetAsync(rp.work_counter, 0, sizeof(uint32_t), stream));
+    PT_CUDA(h, launch(h, rp, stream));
+    if (!block_cost) h->samples.fetch_add((uint64_t)n_blocks * 32u * spp);  // upper bound: edge blocks are partly outside the frame
+    h->launches.fetch_add(1);
+    return PT_OK;
+}
+
 int render_tiles(ptcore *h, const PtTile *tiles, int32_t n_tiles, cudaStream_t stream) {
     if (!h->have_scene) return fail(h, PT_ERR_NO_SCENE, "no scene uploaded");
     if (!h->fb_rgb) return fail(h, PT_ERR_NO_FRAMEBUFFER, "no framebuffer bound");
@@ -212,6 +250,10 @@ int render_tiles(ptcore *h, const PtTile *tiles, int32_t n_tiles, cudaStream_t s
         rp.fb_rgb = h->fb_rgb;
         rp.fb_yuv = h->fb_yuv;
         rp.counters = h->d_counters;
+        rp.block_list = nullptr;
+        rp.n_blocks = 0;
+        rp.pad2 = 0;
+        rp.block_cost = nullptr;
         TileList &tl = rp.tiles;
         tl.n = 0;
         tl.first_item[0] = 0;
@@ -286,6 +328,7 @@ int ptcore_destroy(ptcore_t *h) {
     if (h->blob.pinned) cudaFreeHost(h->blob.pinned);
     cudaFree(h->own_rgb);
     cudaFree(h->own_yuv);
+    cudaFree(h->ident_blocks);
     delete h;
     return PT_OK;
 }
@@ -530,6 +573,32 @@ int ptcore_render_tile_async(ptcore_t *h, int32_t ox, int32_t oy, int32_t w, int
 int ptcore_render_tiles_async(ptcore_t *h, const PtTile *tiles, int32_t n, void *stream) {
     if (!h || (n > 0 && !tiles) || n < 0) return fail(h, PT_ERR_INVALID_ARGUMENT, "bad tile list");
     return render_tiles(h, tiles, n, (cudaStream_t)stream);
+}
+
+int ptcore_render_blocks_async(ptcore_t *h, const uint32_t *blocks_dev, uint32_t n_blocks, void *stream) {
+    if (!h || (n_blocks && !blocks_dev)) return fail(h, PT_ERR_INVALID_ARGUMENT, "bad block list");
+    return render_blocks(h, blocks_dev, n_blocks, h->spp, nullptr, (cudaStream_t)stream);
+}
+
+int ptcore_block_costs_async(ptcore_t *h, uint32_t pilot_spp, uint32_t *costs_dev, void *stream) {
+    if (!h || !costs_dev || pilot_spp == 0) return fail(h, PT_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (!h->fb_rgb) return fail(h, PT_ERR_NO_FRAMEBUFFER, "no framebuffer bound");
+    PT_CUDA(h, cudaSetDevice(h->device));
+    const uint32_t bw = (h->fb_w + 7) / 8, bh = (h->fb_h + 3) / 4, n = bw * bh;
+    // the identity block list lives next to the cost map: costs_dev[n .. 2n)
+    if (h->ident_blocks_n != n) {
+        std::vector<uint32_t> ident(n);
+        for (uint32_t by = 0; by < bh; by++)
+            for (uint32_t bx = 0; bx < bw; bx++) ident[by * bw + bx] = bx | (by << 16);
+        cudaFree(h->ident_blocks);
+        h->ident_blocks = nullptr;
+        h->ident_blocks_n = 0;
+        PT_CUDA(h, cudaMalloc(&h->ident_blocks, sizeof(uint32_t) * n));
+        PT_CUDA(h, cudaMemcpy(h->ident_blocks, ident.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+        h->ident_blocks_n = n;
+    }
+    PT_CUDA(h, cudaMemsetAsync(costs_dev, 0, sizeof(uint32_t) * n, (cudaStream_t)stream));
+    return render_blocks(h, h->ident_blocks, n, pilot_spp, costs_dev, (cudaStream_t)stream);
 }
 
 int ptcore_sync(ptcore_t *h, void *stream) {

@@ -85,6 +85,38 @@ class RankRenderer:
         for s in self.streams:
             cur.wait_stream(s)
         if world > 1 and gather:
-            import torch.distributed as dist
-            dist.reduce(self.rgb, dst=0, op=dist.ReduceOp.SUM)
-            dist.reduce(self.yuv, dst=0, op=dist.ReduceOp.SUM)
+            self._gather()
+
+    def _gather(self) -> None:
+        import torch.distributed as dist
+        dist.reduce(self.rgb, dst=0, op=dist.ReduceOp.SUM)
+        dist.reduce(self.yuv, dst=0, op=dist.ReduceOp.SUM)
+
+    def render_frame_lpt(self, rank: int, world: int, pilot_spp: int = 4, gather: bool = True) -> None:
+        """Cost-sorted block scheduling (longest processing time first).
+
+        Every pixel is one sequential chain of spp samples (its XORWOW stream), so the unit of work cannot be split and
+        a frame ends when the last chain ends.  A pilot pass (pilot_spp samples of every pixel, a few per mille of the
+        frame) measures rays per 8x4 block; blocks are sorted by that cost, dealt round-robin to the ranks (equal cost
+        per GPU without any exchange: every rank computes the same map and the same order) and each GPU's persistent
+        kernel takes its blocks most-expensive-first, which keeps the tail of the frame short.
+        """
+        cur = torch.cuda.current_stream(self.device)
+        s = self.streams[0]
+        s.wait_stream(cur)
+        bw, bh = (self.width + 7) // 8, (self.height + 3) // 4
+        if getattr(self, "costs", None) is None or self.costs.numel() != bw * bh:
+            self.costs = torch.zeros(bw * bh, dtype=torch.int32, device=self.device)
+        with torch.cuda.stream(s):
+            if world > 1:
+                self.rgb.zero_()
+                self.yuv.zero_()
+            self.pt.block_costs_async(pilot_spp, self.costs.data_ptr(), s.cuda_stream)
+            order = torch.argsort(self.costs, descending=True, stable=True)
+            mine = order[rank::world]
+            self.blocks = ((mine % bw) | ((mine // bw) << 16)).to(torch.int32).contiguous()  # kept alive until the next frame
+            self.pt.render_blocks_async(self.blocks.data_ptr(), int(self.blocks.numel()), s.cuda_stream)
+        self.launches += 2
+        cur.wait_stream(s)
+        if world > 1 and gather:
+            self._gather()

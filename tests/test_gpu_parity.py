@@ -175,6 +175,34 @@ def test_run_to_run_determinism_and_tile_invariance(tracer, duck, ptb):
     assert np.array_equal(fy.cpu().numpy(), yfull)
 
 
+def test_block_lists_and_cost_sorted_order_give_the_same_image(tracer, duck, ptb):
+    """ptcore_render_blocks_async (explicit 8x4 block list, any order, any split) and the pilot cost map."""
+    import torch
+    w, h, spp, depth = 150, 70, 5, 8  # ragged: edge blocks are clipped
+    full, yfull = render(tracer, duck, w, h, spp, depth)
+    fb = torch.zeros(h * w * 3, dtype=torch.uint8, device="cuda")
+    fy = torch.zeros(h * w * 3 // 2, dtype=torch.uint8, device="cuda")
+    tracer.bind_framebuffer(fb.data_ptr(), fy.data_ptr(), w, h)
+    bw, bh = (w + 7) // 8, (h + 3) // 4
+    costs = torch.zeros(bw * bh, dtype=torch.int32, device="cuda")
+    tracer.block_costs_async(4, costs.data_ptr())
+    tracer.wait()
+    assert not fb.any()  # the pilot pass stores no pixel
+    c = costs.cpu().numpy().reshape(bh, bw)
+    assert c.min() >= 0 and c.sum() > 4 * w * h  # at least one ray per sample
+    assert c[-1].max() <= c.max()  # top rows see the light/ceiling; just a sanity bound
+    order = torch.argsort(costs, descending=True, stable=True)
+    packed = ((order % bw) | ((order // bw) << 16)).to(torch.int32).contiguous()
+    a, b = packed[0::2].contiguous(), packed[1::2].contiguous()  # what two ranks would render
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    tracer.render_blocks_async(a.data_ptr(), a.numel(), s1.cuda_stream)
+    tracer.render_blocks_async(b.data_ptr(), b.numel(), s2.cuda_stream)
+    tracer.sync(s1.cuda_stream)
+    tracer.sync(s2.cuda_stream)
+    assert np.array_equal(fb.cpu().numpy().reshape(h, w, 3), full)
+    assert np.array_equal(fy.cpu().numpy()[: w * h], yfull[: w * h])
+
+
 def test_tile_offsets_are_bottom_up(tracer, duck):
     import torch
     w, h = 64, 36

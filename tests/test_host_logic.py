@@ -1,0 +1,244 @@
+"""Host-side logic that needs no GPU: the C ABI library loads and exports what include/ptcore.h declares, scene
+ingestion (own GLB / PNG / OBJ readers, .ptscene round trip), the host SAH BVH, float-vs-double folding used by the
+kernels, and the loud failure without a CUDA device."""
+import base64
+import ctypes as C
+import json
+import re
+import struct
+import subprocess
+import zlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, ROOT
+
+
+def declared_functions():
+    text = (ROOT / "include" / "ptcore.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:ptcore|ptscene|pt)_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(core_lib):
+    names = declared_functions()
+    assert len(names) >= 28 and "ptcore_render_tile_async" in names and "pt_tileq_claim" in names
+    for n in names:
+        assert hasattr(core_lib, n), f"libptcore.so does not export {n}"
+    assert core_lib.ptcore_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_a_device(ptb, core_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(ptb.PtError) as e:
+        ptb.PathTracer(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_package_never_imports_the_oracle():
+    """The product may not import, link, call or execute anything under oracle/ (comments naming it are fine)."""
+    pkg = ROOT / "multi-gpu-path-tracer_b200"
+    forbidden = ("pt_oracle", "libpt_oracle", "import _oracle", "pto_", "oracle/_ref", "oracle/_build", "ref_cpu", "ref_gpu")
+    files = [f for ext in ("*.py", "*.h", "*.cpp", "*.cu", "*.cuh") for f in pkg.rglob(ext)]
+    assert len(files) > 15
+    for f in files:
+        text = f.read_text(errors="replace")
+        for bad in forbidden:
+            assert bad not in text, (f, bad)
+        assert not re.search(r'#\s*include\s*[<"][^>"]*oracle', text), f
+
+
+def test_struct_layouts_match_the_header(ptb):
+    assert C.sizeof(ptb.PtMaterial) == 44 and C.sizeof(ptb.PtCamera) == 32 and C.sizeof(ptb.PtTile) == 16
+    assert C.sizeof(ptb.PtStats) == 6 * 8 + 4 * 4 + 8 + 8 + 8
+
+
+# ------------------------------------------------------------------ scene ingestion
+def test_duck_fixture_matches_survey_appendix_a(duck):
+    # SURVEY Appendix A pins (the reference pins nothing at the assimp boundary)
+    assert duck.tri_pos.shape == (4224, 9) and len(duck.mats) == 5 and len(duck.textures) == 1
+    assert np.bincount(duck.tri_mat, minlength=5).tolist() == [2, 6, 2, 2, 4212]
+    lo, hi = duck.tri_pos.reshape(-1, 3).min(0), duck.tri_pos.reshape(-1, 3).max(0)
+    assert np.allclose(lo, [-298.21, -215.13, -1246.35], atol=0.01) and np.allclose(hi, [257.79, 339.58, -687.15], atol=0.01)
+    assert np.allclose(duck.tri_pos[8], [109.791084, 338.58173, -861.65204, -150.20908, 338.5817, -861.65204, -150.20908, 338.58167, -1071.6521], atol=2e-4)
+    assert np.allclose(duck.tri_uv[12], [0.866606, 0.398924, 0.871384, 0.397619, 0.87416, 0.398826], atol=1e-6)
+    assert np.allclose(duck.mats["base"], [[0, 0.5, 0], [0.4, 0.4, 0.4], [0, 0, 0], [0.5, 0, 0], [1, 1, 1]])
+    assert duck.mats["emis"].tolist() == [[0, 0, 0], [0, 0, 0], [1, 1, 1], [0, 0, 0], [0, 0, 0]]
+    assert duck.mats["base_tex"].tolist() == [-1, -1, -1, -1, 0] and duck.textures[0].shape == (512, 512, 3)
+    p = duck.tri_pos[8].reshape(3, 3).astype(np.float64)
+    assert abs(0.5 * np.linalg.norm(np.cross(p[1] - p[0], p[2] - p[0])) - 27300.02) < 0.05
+
+
+def test_box_fixture_has_no_emitter(box):
+    assert box.tri_pos.shape == (36, 9) and np.bincount(box.tri_mat, minlength=5).tolist() == [6, 2, 2, 24, 2]
+    assert not box.mats["emis"].any()
+
+
+def _png(w, h, rgb, palette=False):
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data))
+    if palette:
+        colours = sorted({tuple(p) for p in rgb.reshape(-1, 3)})
+        idx = np.array([colours.index(tuple(p)) for p in rgb.reshape(-1, 3)], np.uint8).reshape(h, w)
+        raw = b"".join(b"\x00" + idx[y].tobytes() for y in range(h))
+        body = chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 3, 0, 0, 0)) + chunk(b"PLTE", bytes(sum(colours, ()))) + chunk(b"IDAT", zlib.compress(raw))
+    else:
+        # filter type 1 (sub) on odd rows to exercise the unfilter
+        rows = []
+        for y in range(h):
+            row = rgb[y].astype(np.int32).reshape(-1)
+            if y % 2:
+                prev = np.concatenate([np.zeros(3, np.int32), row[:-3]])
+                rows.append(b"\x01" + ((row - prev) % 256).astype(np.uint8).tobytes())
+            else:
+                rows.append(b"\x00" + row.astype(np.uint8).tobytes())
+        body = chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"".join(rows)))
+    return b"\x89PNG\r\n\x1a\n" + body + chunk(b"IEND", b"")
+
+
+def _glb(tmp_path, palette):
+    """two nodes (parent scale+translate, child rotate) with one textured quad and one emissive triangle"""
+    pos = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32)
+    uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32)
+    idx = np.array([0, 1, 2, 0, 2, 3], np.uint16)
+    tri = np.array([[0, 0, 1], [1, 0, 1], [0, 1, 1]], np.float32)
+    tex = (np.arange(4 * 3 * 3) * 7 % 256).astype(np.uint8).reshape(3, 4, 3)
+    png = _png(4, 3, tex, palette)
+    blobs, views = b"", []
+    for b in (pos.tobytes(), uv.tobytes(), idx.tobytes(), tri.tobytes(), png):
+        views.append({"buffer": 0, "byteOffset": len(blobs), "byteLength": len(b)})
+        blobs += b + b"\x00" * (-len(b) % 4)
+    s = float(np.sqrt(0.5))
+    gltf = {
+        "asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0, 2]}],
+        "nodes": [{"children": [1], "scale": [2, 2, 2], "translation": [10, 0, 0]}, {"mesh": 0, "rotation": [0, 0, s, s]}, {"mesh": 1}],
+        "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "TEXCOORD_0": 1}, "indices": 2, "material": 1}]},
+                   {"primitives": [{"attributes": {"POSITION": 3}, "material": 0}]}],
+        "materials": [{"name": "Light", "emissiveFactor": [1, 0.5, 0.25], "pbrMetallicRoughness": {"baseColorFactor": [0, 0, 0, 1]}},
+                      {"name": "tex", "pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}}],
+        "textures": [{"source": 0}], "images": [{"bufferView": 4, "mimeType": "image/png"}],
+        "accessors": [{"bufferView": 0, "componentType": 5126, "count": 4, "type": "VEC3"}, {"bufferView": 1, "componentType": 5126, "count": 4, "type": "VEC2"},
+                      {"bufferView": 2, "componentType": 5123, "count": 6, "type": "SCALAR"}, {"bufferView": 3, "componentType": 5126, "count": 3, "type": "VEC3"}],
+        "bufferViews": views, "buffers": [{"byteLength": len(blobs)}],
+    }
+    js = json.dumps(gltf).encode()
+    js += b" " * (-len(js) % 4)
+    glb = struct.pack("<III", 0x46546C67, 2, 12 + 8 + len(js) + 8 + len(blobs)) + struct.pack("<II", len(js), 0x4E4F534A) + js + struct.pack("<II", len(blobs), 0x004E4942) + blobs
+    path = tmp_path / ("scene_p.glb" if palette else "scene.glb")
+    path.write_bytes(glb)
+    return path, tex
+
+
+@pytest.mark.parametrize("palette", [False, True])
+def test_glb_loader_bakes_transforms_orders_by_material_flips_v_and_decodes_png(ptb, core_lib, tmp_path, palette):
+    path, tex = _glb(tmp_path, palette)
+    sc = ptb.load_scene_file(path)
+    # material-index order (assimp PreTransformVertices): the emissive triangle (material 0) first, then the quad (material 1)
+    assert sc.tri_mat.tolist() == [0, 1, 1]
+    assert np.allclose(sc.tri_pos[0], [0, 0, 1, 1, 0, 1, 0, 1, 1])
+    # quad: rotate 90 deg about z, scale 2, translate (10,0,0): (x,y,0) -> (10 - 2y, 2x, 0)
+    assert np.allclose(sc.tri_pos[1], [10, 0, 0, 10, 2, 0, 8, 2, 0], atol=1e-5)
+    assert np.allclose(sc.tri_uv[1], [0, 1, 1, 1, 1, 0])  # V flipped to 1 - v
+    assert sc.mats["emis"][0].tolist() == [1, 0.5, 0.25] and sc.mats["base"][1].tolist() == [1, 1, 1]  # baseColorFactor default (1,1,1)
+    assert sc.mats["base_tex"].tolist() == [-1, 0]
+    assert np.array_equal(sc.textures[0], tex.astype(np.float32))
+    ok, msg, _ = ptb.bvh_selftest(sc)
+    assert ok, msg
+
+
+def test_obj_loader_routes_materials_by_name_prefix(ptb, core_lib, tmp_path):
+    # reference README.md:60-76 / src/obj_loader.h:65-96
+    (tmp_path / "m.mtl").write_text("newmtl lambertian_red\nKa 0.5 0.1 0.1\nnewmtl metal_a\nKa 0.8 0.8 0.9\nNs 0.3\nnewmtl dielectric_g\nNi 1.5\n"
+                                    "newmtl diffuse_light_top\nKd 4 4 4\nnewmtl plain\nKd 0.2 0.3 0.4\nKe 1 1 1\n")
+    (tmp_path / "s.obj").write_text("mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\n"
+                                    "usemtl lambertian_red\nf 1/1 2/2 3/3 4/4\nusemtl metal_a\nf 1 2 3\nusemtl dielectric_g\nf -4 -3 -2\n"
+                                    "usemtl diffuse_light_top\nf 1 3 4\nusemtl plain\nf 1//1 2//1 4//1\nl 1 2\n")
+    sc = ptb.load_scene_file(tmp_path / "s.obj")
+    assert sc.tri_mat.tolist() == [0, 0, 1, 2, 3, 4]  # the quad is fan-triangulated, the line is dropped
+    assert sc.mats["type"].tolist() == [ptb.PT_MAT_LAMBERTIAN, ptb.PT_MAT_METAL, ptb.PT_MAT_DIELECTRIC, ptb.PT_MAT_DIFFUSE_LIGHT, ptb.PT_MAT_UNIVERSAL]
+    assert np.allclose(sc.mats["base"][0], [0.5, 0.1, 0.1]) and np.isclose(sc.mats["fuzz"][1], 0.3) and np.isclose(sc.mats["ior"][2], 1.5)
+    assert sc.mats["emis"][3].tolist() == [4, 4, 4] and sc.mats["emis"][4].tolist() == [1, 1, 1] and np.allclose(sc.mats["base"][4], [0.2, 0.3, 0.4])
+    assert np.allclose(sc.tri_uv[0], [0, 0, 1, 0, 1, 1])
+
+
+def test_unknown_and_broken_files_raise(ptb, core_lib, tmp_path):
+    (tmp_path / "a.fbx").write_text("x")
+    (tmp_path / "b.glb").write_bytes(b"glTF" + b"\x00" * 30)
+    for f in ("a.fbx", "b.glb", "missing.glb"):
+        with pytest.raises(ptb.PtError):
+            ptb.load_scene_file(tmp_path / f)
+
+
+def test_ptscene_round_trip_python_and_native(ptb, core_lib, duck, tmp_path):
+    raw = duck.to_ptscene_bytes()
+    again = ptb.Scene.from_ptscene_bytes(raw)
+    assert again.to_ptscene_bytes() == raw
+    flat = tmp_path / "duck.ptscene"
+    flat.write_bytes(raw)
+    native = ptb.load_scene_file(flat)  # .ptscene through Python
+    tool = ROOT / "multi-gpu-path-tracer_b200" / "_lib" / "ptscene_tool"
+    if tool.exists():
+        out = tmp_path / "again.ptscene"
+        info = json.loads(subprocess.run([str(tool), "convert", str(flat), str(out)], check=True, capture_output=True, text=True).stdout)
+        assert info["triangles"] == 4224 and info["per_material"] == [2, 6, 2, 2, 4212]
+        assert out.read_bytes() == raw  # native reader + writer reproduce the file byte for byte
+    assert np.array_equal(native.tri_pos, duck.tri_pos)
+
+
+# ------------------------------------------------------------------ BVH
+def test_bvh_is_structurally_valid_for_fixtures_and_edge_cases(ptb, core_lib, duck, box):
+    for scene, leaf in ((duck, 4), (duck, 1), (duck, 8), (box, 4), (box, 2)):
+        ok, msg, st = ptb.bvh_selftest(scene, leaf)
+        assert ok, msg
+        assert st["bvh_depth"] <= 48 and st["bvh_leaves"] >= len(scene.tri_mat) / leaf
+    ok, msg, st = ptb.bvh_selftest(duck, 4)
+    assert 1500 < st["bvh_nodes"] < 4224 and st["bvh_depth"] < 30
+    rng = np.random.default_rng(1)
+    mats = np.zeros(1, ptb.MAT_DTYPE)
+    mats["type"] = ptb.PT_MAT_UNIVERSAL
+    cases = {
+        "empty": np.zeros((0, 9), np.float32),
+        "single": rng.random((1, 9), dtype=np.float32),
+        "all coincident": np.tile(rng.random((1, 9), dtype=np.float32), (37, 1)),
+        "collinear centroids": np.stack([np.concatenate([[i, 0, 0], [i + .5, 0, 0], [i, .5, 0]]) for i in range(200)]).astype(np.float32),
+        "huge range": (rng.random((500, 9), dtype=np.float32) * np.float32(1e6)) ** 2,
+    }
+    for name, pos in cases.items():
+        sc = ptb.Scene(tri_pos=pos, tri_uv=np.zeros((len(pos), 6), np.float32), tri_mat=np.zeros(len(pos), np.int32), mats=mats)
+        ok, msg, st = ptb.bvh_selftest(sc, 4)
+        assert ok, (name, msg)
+    sph = ptb.Scene(sph=np.array([[0, 0, 0, 1], [3, 0, 0, 0.5], [0, -1000, 0, 999]], np.float32), sph_mat=np.zeros(3, np.int32), mats=mats)
+    ok, msg, st = ptb.bvh_selftest(sph, 4)
+    assert ok, msg
+
+
+# ------------------------------------------------------------------ arithmetic folds used by the kernels
+def test_double_literal_comparisons_fold_to_float():
+    # pt_device.cuh: x < 1e-8 (double)  <=>  x < 1.00000008274037e-08f ;  x > 0.0001 (double)  <=>  x > 0.0001f
+    eps_up = np.float32(1.00000008274037e-08)
+    around = np.float32(1e-8)
+    xs = [np.nextafter(around, np.float32(0), dtype=np.float32), around, np.nextafter(around, np.float32(1), dtype=np.float32), eps_up]
+    x = xs[0]
+    for _ in range(8):
+        x = np.nextafter(x, np.float32(0), dtype=np.float32)
+        xs.append(x)
+    for x in xs:
+        for sgn in (1, -1):
+            v = np.float32(sgn) * x
+            assert (float(v) < 1e-8 and float(v) > -1e-8) == bool(v < eps_up and v > -eps_up), v
+    t = np.float32(0.0001)
+    for x in (np.nextafter(t, np.float32(0), dtype=np.float32), t, np.nextafter(t, np.float32(1), dtype=np.float32)):
+        assert (float(x) > 0.0001) == bool(x > t)
+
+
+def test_exhaustive_exactness_of_reciprocal_and_div_by_pi(tmp_path):
+    """(float)(1.0/(double)x) == 1.0f/x for every positive normal float; the 3-op double evaluation of c / M_PI
+    equals the IEEE double division for every float c in [0, 4]: tests/c/exactness_check.c (about 3 G cases, OpenMP)."""
+    exe = tmp_path / "exactness_check"
+    subprocess.run(["/usr/bin/gcc", "-O2", "-ffp-contract=off", "-fopenmp", str(ROOT / "tests" / "c" / "exactness_check.c"), "-lm", "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, timeout=600).stdout
+    assert "double mismatches 0, float-result mismatches 0" in out and "rcp:" in out and out.strip().endswith("mismatches 0"), out
