@@ -334,16 +334,12 @@ def main():
             t0 = time.perf_counter()
             h2d = pt.reupload_scene() + 32  # compiled scene blob from pinned host memory + the camera struct
             pt.set_camera()
-            if world == 1:
-                pt.render_frame_host(WIDTH, HEIGHT, True, rgb_np, yuv_np)
+            render_frame()
+            if rank == 0:
+                rgb_host.view(-1).copy_(rr.rgb, non_blocking=True)
+                yuv_host.copy_(rr.yuv, non_blocking=True)
                 d2h = rgb_np.nbytes + yuv_np.nbytes
-            else:
-                render_frame()
-                if rank == 0:
-                    rgb_host.view(-1).copy_(rr.rgb, non_blocking=True)
-                    yuv_host.copy_(rr.yuv, non_blocking=True)
-                    d2h = rgb_np.nbytes + yuv_np.nbytes
-                torch.cuda.synchronize(device)
+            torch.cuda.synchronize(device)
             barrier()
             return time.perf_counter() - t0
 
@@ -354,8 +350,6 @@ def main():
             tt = torch.tensor([tsum], dtype=torch.float64, device=device)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             tsum = float(tt[0])
-        if world > 1:
-            pt.bind_framebuffer(rr.rgb.data_ptr(), rr.yuv.data_ptr(), WIDTH, HEIGHT)
         e2e = {"value": samples_per_step * args.steps / tsum / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1000.0 * tsum / args.steps}
 
