@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--min-blocks", type=int, default=0)
     ap.add_argument("--sched", default="lpt", choices=["lpt", "tiles"], help="lpt: pilot pass + cost-sorted 8x4 blocks dealt round-robin to the ranks; tiles: dynamic tile claims")
     ap.add_argument("--pilot-spp", type=int, default=4)
+    ap.add_argument("--emulate-world", type=int, default=0, help="experiments: render only rank 0's share of an N-rank frame on one GPU")
     ap.add_argument("--tile", default="64x32")
     ap.add_argument("--claim", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -257,7 +258,7 @@ def main():
 
     def render_frame():
         if args.sched == "lpt" and args.kernel == "persistent":
-            rr.render_frame_lpt(rank, world, args.pilot_spp)
+            rr.render_frame_lpt(rank, args.emulate_world or world, args.pilot_spp, gather=not args.emulate_world)
         else:
             rr.render_frame(plan, queue, rank, world)
 

@@ -244,13 +244,16 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) pt_wavefront_kernel(const
         // ---------------- TRAVERSE (warp-synchronous wavefront over uniform steps) ----------------
         // lanes with a path are either still traversing (one of the two votes below is true) or finished and waiting
         const int n_paths = __popc(__ballot_sync(kFullMask, have_path));
+        // near the end of a launch a warp has few lanes left: scale the threshold so that finished lanes never wait for
+        // more lanes than exist (otherwise the survivors advance in per-ray lock-step and the tail of the frame doubles)
+        const int wait_for = min(refill_at, max(1, (n_paths * 3) >> 2));
         for (;;) {
             const bool can_node = tr.cur >= 0;
             const bool can_prim = tr.leaf_left > 0;
             const unsigned m_node = __ballot_sync(kFullMask, can_node);
             const unsigned m_prim = __ballot_sync(kFullMask, can_prim);
             const int n_active = __popc(m_node | m_prim);
-            if (n_active == 0 || n_paths - n_active >= refill_at) break;
+            if (n_active == 0 || n_paths - n_active >= wait_for) break;
             if (__popc(m_node) >= __popc(m_prim)) {
                 for (int k = 0; k < node_burst; k++)
                     if (tr.cur >= 0) trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
