@@ -43,8 +43,9 @@ def compare(rgb, ref, spp):
     return dict(frac_within_1=frac1, identical=float((d.max(axis=2) == 0).mean()), mad=mad, rmse=rmse, bound=1 - 1.5e-3 * spp - 0.005)
 
 
-def check(rgb, ref, spp):
+def check(rgb, ref, spp, rate=1.5e-3):
     m = compare(rgb, ref, spp)
+    m["bound"] = 1 - rate * spp - 0.005
     assert m["frac_within_1"] >= m["bound"], m
     assert m["mad"] <= 0.50, m
     assert m["rmse"] <= (6.0 if spp <= 16 else 3.0), m
@@ -201,6 +202,38 @@ def test_block_lists_and_cost_sorted_order_give_the_same_image(tracer, duck, ptb
     tracer.sync(s2.cuda_stream)
     assert np.array_equal(fb.cpu().numpy().reshape(h, w, 3), full)
     assert np.array_equal(fy.cpu().numpy()[: w * h], yfull[: w * h])
+
+
+def test_spheres_and_rtow_materials_match_oracle(tracer, oracle, ptb):
+    """sphere test, lambertian / metal / dielectric / diffuse_light scatter and the builder-defined glue,
+    mixed with UNIVERSAL surfaces, a textured quad and an importance-sampled area light.  No reference renderer exists for
+    these (dead code there), so the oracle is the only checker; glass and metal paths are chaotic, hence the wider rate."""
+    sc, cam = ptb.scenes.mixed_material_test_scene()
+    rgb, yuv = render(tracer, sc, 80, 45, 8, 8, cam)
+    ref, _, ost = oracle.render(sc, 80, 45, 8, 8, camera=cam)
+    m = check(rgb, ref, 8, rate=4e-3)
+    st = tracer.stats()
+    assert abs(st["rays"] - ost["rays"]) <= 0.02 * ost["rays"]
+    a, _ = render(tracer, sc, 80, 45, 8, 8, cam, kernel=ptb.PT_KERNEL_DIRECT, ptb=ptb)
+    assert np.array_equal(a, rgb)
+    tracer.set_option(ptb.PT_OPT_KERNEL, ptb.PT_KERNEL_PERSISTENT)
+    print(m)
+
+
+def test_sphere_field_config3_matches_oracle(tracer, oracle, ptb):
+    sc, cam = ptb.scenes.rtow_sphere_field()
+    rgb, _ = render(tracer, sc, 96, 54, 4, 10, cam)
+    ref, _, _ = oracle.render(sc, 96, 54, 4, 10, camera=cam)
+    print(check(rgb, ref, 4, rate=6e-3))
+
+
+def test_displaced_mesh_config4_matches_oracle(tracer, oracle, duck, ptb):
+    sc = ptb.scenes.displaced_sphere_in_cornell(duck, n=96)
+    rgb, _ = render(tracer, sc, 96, 54, 4, 8)
+    ref, _, _ = oracle.render(sc, 96, 54, 4, 8)
+    print(check(rgb, ref, 4, rate=3e-3))
+    st = tracer.stats()
+    assert st["bvh_depth"] <= 48 and st["bvh_nodes"] > 4000
 
 
 def test_tile_offsets_are_bottom_up(tracer, duck):
