@@ -375,21 +375,23 @@ __device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, int3
     float rf = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), t.best.t));
     const bool hl = ln <= lf * kSlack;
     const bool hr = rn <= rf * kSlack;
+    // Successor selection with predication instead of nested branches (this tail was 17 % of all executed instructions at
+    // 10 active threads per instruction in profiles/r01_ncu_wavefront_final_*.txt):
     const bool both = hl & hr;
+    const bool any = hl | hr;
     const bool rightNear = hr & (!hl | (rn < ln));
-    int32_t next = rightNear ? refs.y : refs.x;
-    const int32_t other = rightNear ? refs.x : refs.y;
-    if (hl | hr) {
-        if (next < 0 && t.leaf_left == 0) {  // reached a leaf and the slot is free: hold it, keep descending elsewhere
-            trav_hold_leaf(t, next);
-            next = both ? other : stack[--t.sp];
-        } else if (both) {
-            stack[t.sp++] = other;
-        }
-    } else {
-        next = stack[--t.sp];
-    }
-    if (next < 0 && next != kTravDone && t.leaf_left == 0) {  // the popped entry is a leaf and the slot is free
+    const int32_t nearRef = rightNear ? refs.y : refs.x;
+    const int32_t farRef = rightNear ? refs.x : refs.y;
+    const bool holdNear = any & (nearRef < 0) & (t.leaf_left == 0);  // reached a leaf and the slot is free: hold it
+    const bool needPush = both & !holdNear;
+    const bool needPop = !any | (holdNear & !both);
+    if (needPush) stack[t.sp] = farRef;
+    t.sp += needPush ? 1 : 0;
+    t.sp -= needPop ? 1 : 0;
+    int32_t next = holdNear ? farRef : nearRef;
+    if (needPop) next = stack[t.sp];
+    if (holdNear) trav_hold_leaf(t, nearRef);
+    if (next < 0 && next != kTravDone && t.leaf_left == 0) {  // the successor is itself a leaf and the slot is (still) free
         trav_hold_leaf(t, next);
         next = stack[--t.sp];
     }
