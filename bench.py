@@ -33,6 +33,21 @@ FLOPS_PER_RAY = lambda n_box, n_tri: 24.0 * n_box + 45.0 * n_tri + 180.0
 BYTES_PER_RAY = lambda n_box, n_tri: 32.0 * n_box + 48.0 * n_tri + 168.0
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE pt_wavefront_kernel launch on the default workload (1 GPU), from the
+    committed `ncu --set full` summary (profiles/r01_ncu_wavefront_final_1080p_1024spp.txt); None if absent."""
+    p = ROOT / "profiles" / "r01_ncu_wavefront_final_1080p_1024spp.txt"
+    if not p.exists():
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    for ln in p.read_text().splitlines():
+        f = ln.split()
+        if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[1] in scale:
+            total += float(f[2]) * scale[f[1]]
+    return total or None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -188,7 +203,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
+                    help="config2 (default, the bench line): 1080p/1024 spp; config5: 3840x2160/4096 spp, the strong-scaling case of BASELINE.json (a parity-test case, not the bench line)")
     args = ap.parse_args()
+    global WIDTH, HEIGHT, SPP, WORKLOAD
+    if args.workload == "config5":
+        WIDTH, HEIGHT, SPP = 3840, 2160, 4096
+        WORKLOAD = f"cornell_duck {WIDTH}x{HEIGHT} spp={SPP} depth={DEPTH} (BASELINE configs[4])"
+        if args.spp == 1024:
+            args.spp = SPP
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -364,7 +387,8 @@ def main():
         sm_mhz = (clocks or {}).get("sm_mhz") or peaks["sm_max_mhz"]
         fp32_peak_max = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
         roofline = {"bound": "hbm", "achieved": abytes / (kernel_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": abytes / (kernel_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "kernel": {"persistent": "pt_wavefront_kernel", "direct": "pt_direct_kernel", "lockstep": "pt_persistent_kernel"}[args.kernel],
+                    "frac": abytes / (kernel_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                    "traffic": ncu_traffic_bytes() if (world == 1 and spp == SPP and args.kernel == "persistent") else None, "algorithmic_bytes_per_launch": abytes, "kernel": {"persistent": "pt_wavefront_kernel", "direct": "pt_direct_kernel", "lockstep": "pt_persistent_kernel"}[args.kernel],
                     "peak_source": peaks["source"], "algorithmic_bytes_per_ray": BYTES_PER_RAY(per_ray["box"], per_ray["tri"]),
                     "note": "algorithmic bytes are node/triangle fetches served by L1/L2 on this 1.5 MB scene; the binding roof is FP32 issue (roofline_fp32)"}
         roofline_fp32 = {"bound": "fp32", "achieved": aflops / (kernel_ms / 1e3) / 1e12, "peak": fp32_peak_max, "unit": "TFLOP/s",
