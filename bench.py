@@ -184,6 +184,7 @@ def run_reference_arm(args, rank):
 
 
 def main():
+    global WIDTH, HEIGHT, SPP, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -206,7 +207,6 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
                     help="config2 (default, the bench line): 1080p/1024 spp; config5: 3840x2160/4096 spp, the strong-scaling case of BASELINE.json (a parity-test case, not the bench line)")
     args = ap.parse_args()
-    global WIDTH, HEIGHT, SPP, WORKLOAD
     if args.workload == "config5":
         WIDTH, HEIGHT, SPP = 3840, 2160, 4096
         WORKLOAD = f"cornell_duck {WIDTH}x{HEIGHT} spp={SPP} depth={DEPTH} (BASELINE configs[4])"
