@@ -105,7 +105,8 @@ enum { /* ptcore_set_option keys */
     PT_OPT_SLICE_SPP = 5,    /* samples a lane runs on one pixel before handing it back to the pool (0 = whole pixel) */
     PT_OPT_REFILL_AT = 6,    /* wavefront kernel: finished lanes per warp that trigger a shade/refill pass (1..32, default 16) */
     PT_OPT_NODE_BURST = 7,   /* wavefront kernel: node steps per warp vote (1..4) */
-    PT_OPT_MIN_BLOCKS = 8    /* wavefront kernel build: __launch_bounds__(128, 6) (80 registers) or (128, 8) (64 registers) */
+    PT_OPT_MIN_BLOCKS = 8,   /* accepted for compatibility: only the __launch_bounds__(128, 8) (64-register) build is shipped */
+    PT_OPT_BVH_WIDTH = 9     /* wavefront kernel: walk the 2-wide (64 B nodes) or the collapsed 4-wide (128 B nodes) tree; default 4 */
 };
 enum {
     PT_KERNEL_PERSISTENT = 0, /* persistent-thread wavefront: per-lane pixel refill + warp-voted uniform traversal steps (default) */
@@ -124,6 +125,7 @@ typedef struct PtStats {
     double bvh_build_ms;  /* host time of the last scene compile */
     double sah_cost;
     uint64_t scene_bytes; /* size of the compiled device blob */
+    uint32_t bvh4_nodes, bvh4_depth; /* the collapsed four-wide tree */
 } PtStats;
 
 /* ---- lifetime (DevicePathTracer ctor/dtor, src/DevicePathTracer.h:169-192,372-377) ---- */

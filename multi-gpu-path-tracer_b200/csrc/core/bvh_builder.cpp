@@ -233,6 +233,15 @@ BvhBuildResult build_bvh(const std::vector<PrimBounds> &bounds, const BvhBuildOp
         n.left = n.right = leaf_ref(0, 1);  // never entered
         out.nodes.push_back(n);
         out.depth = 1;
+        FlatNode4 n4{};
+        for (int c = 0; c < 4; c++) {
+            n4.lox[c] = n4.loy[c] = n4.loz[c] = inf;
+            n4.hix[c] = n4.hiy[c] = n4.hiz[c] = -inf;
+            n4.ref[c] = leaf_ref(0, 1);
+        }
+        out.nodes4.push_back(n4);
+        out.depth4 = 1;
+        out.stack4 = 5;
         return out;
     }
     Builder b(bounds, opt);
@@ -296,6 +305,70 @@ BvhBuildResult build_bvh(const std::vector<PrimBounds> &bounds, const BvhBuildOp
         }
         out.sah_cost += opt.traversal_cost;
     }
+    // ---- collapse to four-wide nodes ----
+    {
+        auto emptySlot = [&](FlatNode4 &n, int c) {
+            n.lox[c] = n.loy[c] = n.loz[c] = inf;
+            n.hix[c] = n.hiy[c] = n.hiz[c] = -inf;
+            n.ref[c] = leaf_ref(0, 1);
+        };
+        auto setSlot = [&](FlatNode4 &n, int c, const Box &bx, int32_t ref) {
+            n.lox[c] = bx.lo[0]; n.hix[c] = bx.hi[0];
+            n.loy[c] = bx.lo[1]; n.hiy[c] = bx.hi[1];
+            n.loz[c] = bx.lo[2]; n.hiz[c] = bx.hi[2];
+            n.ref[c] = ref;
+        };
+        if (b.tmp[0].left < 0) {
+            FlatNode4 n{};
+            for (int c = 0; c < 4; c++) emptySlot(n, c);
+            const TmpNode &t = b.tmp[0];
+            setSlot(n, 0, t.box, leaf_ref(t.first, std::min<int32_t>(t.count, kMaxLeafPrims)));
+            out.nodes4.push_back(n);
+            out.depth4 = 1;
+        } else {
+            struct W { int32_t tmp; int32_t flat; uint32_t depth; };
+            std::vector<W> st;
+            out.nodes4.emplace_back();
+            st.push_back({0, 0, 1});
+            while (!st.empty()) {
+                W w = st.back();
+                st.pop_back();
+                out.depth4 = std::max(out.depth4, w.depth);
+                int32_t kids[4];
+                int nk = 2;
+                kids[0] = b.tmp[(size_t)w.tmp].left;
+                kids[1] = b.tmp[(size_t)w.tmp].right;
+                while (nk < 4) {
+                    int best = -1;
+                    float bestArea = -1.f;
+                    for (int k = 0; k < nk; k++) {
+                        const TmpNode &c = b.tmp[(size_t)kids[k]];
+                        if (c.left >= 0 && c.box.half_area() > bestArea) { bestArea = c.box.half_area(); best = k; }
+                    }
+                    if (best < 0) break;
+                    const TmpNode &c = b.tmp[(size_t)kids[best]];
+                    kids[best] = c.left;
+                    kids[nk++] = c.right;
+                }
+                FlatNode4 n{};
+                for (int c = 0; c < 4; c++) emptySlot(n, c);
+                // children that are inner nodes get consecutive flat indices; visit them in slot order (DFS-ish layout)
+                for (int k = nk - 1; k >= 0; k--) {
+                    const TmpNode &c = b.tmp[(size_t)kids[k]];
+                    if (c.left >= 0) {
+                        int32_t fi = (int32_t)out.nodes4.size();
+                        out.nodes4.emplace_back();
+                        setSlot(n, k, c.box, fi);
+                        st.push_back({kids[k], fi, w.depth + 1});
+                    } else {
+                        setSlot(n, k, c.box, leaf_ref(c.first, c.count));
+                    }
+                }
+                out.nodes4[(size_t)w.flat] = n;
+            }
+        }
+        out.stack4 = 3 * out.depth4 + 2;
+    }
     auto t1 = std::chrono::high_resolution_clock::now();
     out.build_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     return out;
@@ -350,6 +423,53 @@ const char *validate_bvh(const BvhBuildResult &bvh, const std::vector<PrimBounds
     for (size_t i = 0; i < n; i++)
         if (!seenPos[i]) return "primitive not reachable from the root";
     if (depth > (uint32_t)kMaxTraversalDepth) return "tree deeper than the device stack";
+    return "";
+}
+
+const char *validate_bvh4(const BvhBuildResult &bvh, const std::vector<PrimBounds> &bounds) {
+    const size_t n = bounds.size();
+    if (bvh.nodes4.empty()) return "no wide nodes";
+    if (n == 0) return "";
+    std::vector<uint8_t> seenPos(n, 0), seenNode(bvh.nodes4.size(), 0);
+    struct W { int32_t node; uint32_t depth; float lo[3], hi[3]; };
+    std::vector<W> st;
+    const float inf = std::numeric_limits<float>::infinity();
+    st.push_back({0, 1, {-inf, -inf, -inf}, {inf, inf, inf}});
+    uint32_t depth = 0;
+    while (!st.empty()) {
+        W w = st.back();
+        st.pop_back();
+        if (w.node < 0 || (size_t)w.node >= bvh.nodes4.size()) return "wide node ref out of range";
+        if (seenNode[(size_t)w.node]) return "wide node reached twice";
+        seenNode[(size_t)w.node] = 1;
+        depth = std::max(depth, w.depth);
+        const FlatNode4 &nd = bvh.nodes4[(size_t)w.node];
+        for (int c = 0; c < 4; c++) {
+            float lo[3] = {nd.lox[c], nd.loy[c], nd.loz[c]}, hi[3] = {nd.hix[c], nd.hiy[c], nd.hiz[c]};
+            if (lo[0] > hi[0]) continue;  // unused slot
+            for (int k = 0; k < 3; k++)
+                if (lo[k] < w.lo[k] || hi[k] > w.hi[k]) return "wide child box not inside parent box";
+            int32_t ref = nd.ref[c];
+            if (ref >= 0) {
+                W cw{ref, w.depth + 1, {lo[0], lo[1], lo[2]}, {hi[0], hi[1], hi[2]}};
+                st.push_back(cw);
+            } else {
+                int32_t v = ~ref, first = v >> kLeafCountBits, count = (v & (kMaxLeafPrims - 1)) + 1;
+                if (first < 0 || (size_t)first + (size_t)count > n) return "wide leaf range out of bounds";
+                for (int32_t i = 0; i < count; i++) {
+                    if (seenPos[(size_t)first + (size_t)i]) return "wide leaf ranges overlap";
+                    seenPos[(size_t)first + (size_t)i] = 1;
+                    const PrimBounds &pb = bounds[(size_t)bvh.prim_order[(size_t)first + (size_t)i]];
+                    for (int k = 0; k < 3; k++)
+                        if (pb.lo[k] < lo[k] || pb.hi[k] > hi[k]) return "primitive not inside its wide leaf box";
+                }
+            }
+        }
+    }
+    for (size_t i = 0; i < n; i++)
+        if (!seenPos[i]) return "primitive not reachable from the wide root";
+    if (depth != bvh.depth4) return "depth4 mismatch";
+    if (bvh.stack4 > 62) return "wide tree needs more stack than the device provides";
     return "";
 }
 

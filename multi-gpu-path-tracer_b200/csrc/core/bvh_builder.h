@@ -31,9 +31,21 @@ struct alignas(64) FlatNode {
 };
 static_assert(sizeof(FlatNode) == 64, "FlatNode must be one 64-byte line");
 
+// Wide node: up to four children, boxes as SoA so that one lane tests all four with independent instruction streams.
+// 128 bytes = eight 16-byte quads; the kernel fetches the first seven.
+//   q[0] = lo.x of children 0..3, q[1] = hi.x, q[2] = lo.y, q[3] = hi.y, q[4] = lo.z, q[5] = hi.z, q[6] = child refs (int32)
+// Built by collapsing the SAH BVH2: a node's inner children are opened (largest surface area first) until it has four
+// children or only leaves.  Unused slots carry an inverted box and are never entered.
+struct alignas(128) FlatNode4 {
+    float lox[4], hix[4], loy[4], hiy[4], loz[4], hiz[4];
+    int32_t ref[4];
+    int32_t pad[4];
+};
+static_assert(sizeof(FlatNode4) == 128, "FlatNode4 must be 128 bytes");
+
 constexpr int kLeafCountBits = 3;
 constexpr int kMaxLeafPrims = 1 << kLeafCountBits;  // 8
-constexpr int kMaxTraversalDepth = 48;              // device stack (per-thread local memory) holds this many entries
+constexpr int kMaxTraversalDepth = 48;              // BVH2 depth bound; the device stack (64 entries) covers it for both node widths
 
 struct PrimBounds {
     float lo[3], hi[3];
@@ -48,6 +60,9 @@ struct BvhBuildOptions {
 
 struct BvhBuildResult {
     std::vector<FlatNode> nodes;       // nodes[0] is the root
+    std::vector<FlatNode4> nodes4;     // the same tree collapsed to four-wide nodes, nodes4[0] is the root
+    uint32_t depth4 = 0;               // depth of the collapsed tree
+    uint32_t stack4 = 0;               // worst-case traversal stack entries of the collapsed tree (3 per level)
     std::vector<int32_t> prim_order;   // leaf-order position -> input primitive index
     uint32_t n_leaves = 0, depth = 0;
     double sah_cost = 0.0;
@@ -60,5 +75,6 @@ BvhBuildResult build_bvh(const std::vector<PrimBounds> &bounds, const BvhBuildOp
 // Structural validation used by the tests: every primitive in exactly one leaf, child boxes
 // enclose their primitives, refs in range, depth within the device stack. Returns "" if valid.
 const char *validate_bvh(const BvhBuildResult &bvh, const std::vector<PrimBounds> &bounds);
+const char *validate_bvh4(const BvhBuildResult &bvh, const std::vector<PrimBounds> &bounds);
 
 }  // namespace ptc

@@ -28,6 +28,7 @@ struct TexDesc {
 
 struct DevScene {
     const float4 *nodes;   // 4 per node     (FlatNode, bvh_builder.h)
+    const float4 *nodes4;  // 8 per wide node (FlatNode4): lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] refs[4] pad
     const float4 *prims;   // 3 per primitive in leaf order:
                            //   triangle: (v0.xyz, e1.x) (e1.yz, e2.xy) (e2.z, -, kind=0, -)
                            //   sphere  : (c.xyz, r)     (-,-,-,-)      (-, -, kind=1, -)
@@ -213,7 +214,7 @@ __device__ __forceinline__ bool sphere_test(float3 center, float radius, float3 
 // t-culled slab tests on both children of a 64-byte node, near child first, stack of far
 // children in per-thread local memory, leaves of <= 8 primitives fetched as 3 x LDG.128.
 // ----------------------------------------------------------------------------------------
-constexpr int kStackSize = 48;
+constexpr int kStackSize = 64;
 
 // Reciprocal direction for the fma-form slab test t = b * inv + (-o * inv).  A zero (or denormal) direction
 // component would give inv = inf and then inf - inf = NaN exactly when the origin lies between the slab planes,
@@ -392,6 +393,49 @@ __device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, int3
     if (needPop) next = stack[t.sp];
     if (holdNear) trav_hold_leaf(t, nearRef);
     if (next < 0 && next != kTravDone && t.leaf_left == 0) {  // the successor is itself a leaf and the slot is (still) free
+        trav_hold_leaf(t, next);
+        next = stack[--t.sp];
+    }
+    t.cur = next;
+}
+
+// one step on a four-wide node (precondition: t.cur >= 0): four independent slab tests, continue with the nearest
+// child that was hit, push the other hit children
+template <bool COUNT>
+__device__ __forceinline__ void trav_node_step4(const DevScene &sc, Trav &t, int32_t *stack, float tmin, uint32_t &n_box) {
+    const float kSlack = 1.0000004f;
+    const float4 *nd = sc.nodes4 + (size_t)t.cur * 8;
+    const float4 lox = __ldg(nd + 0), hix = __ldg(nd + 1), loy = __ldg(nd + 2), hiy = __ldg(nd + 3), loz = __ldg(nd + 4), hiz = __ldg(nd + 5);
+    const int4 refs = __ldg(reinterpret_cast<const int4 *>(nd + 6));
+    if (COUNT) n_box += 4;
+#define PT_SLAB4(c)                                                                                                   \
+    const float ax##c = fmaf(lox.c, t.inv.x, t.oinv.x), bx##c = fmaf(hix.c, t.inv.x, t.oinv.x);                       \
+    const float ay##c = fmaf(loy.c, t.inv.y, t.oinv.y), by##c = fmaf(hiy.c, t.inv.y, t.oinv.y);                       \
+    const float az##c = fmaf(loz.c, t.inv.z, t.oinv.z), bz##c = fmaf(hiz.c, t.inv.z, t.oinv.z);                       \
+    const float tn##c = fmaxf(fmaxf(fminf(ax##c, bx##c), fminf(ay##c, by##c)), fmaxf(fminf(az##c, bz##c), tmin));     \
+    const float tf##c = fminf(fminf(fmaxf(ax##c, bx##c), fmaxf(ay##c, by##c)), fminf(fmaxf(az##c, bz##c), t.best.t)); \
+    const bool h##c = tn##c <= tf##c * kSlack;
+    PT_SLAB4(x)
+    PT_SLAB4(y)
+    PT_SLAB4(z)
+    PT_SLAB4(w)
+#undef PT_SLAB4
+    // entry distances are >= tmin > 0, so their bit patterns order like unsigned integers; the two low mantissa bits
+    // carry the slot number (ordering only steers the walk, it never decides a hit)
+    const uint32_t k0 = hx ? ((__float_as_uint(tnx) & ~3u) | 0u) : 0xffffffffu;
+    const uint32_t k1 = hy ? ((__float_as_uint(tny) & ~3u) | 1u) : 0xffffffffu;
+    const uint32_t k2 = hz ? ((__float_as_uint(tnz) & ~3u) | 2u) : 0xffffffffu;
+    const uint32_t k3 = hw ? ((__float_as_uint(tnw) & ~3u) | 3u) : 0xffffffffu;
+    const uint32_t kmin = min(min(k0, k1), min(k2, k3));
+    const bool any = kmin != 0xffffffffu;
+    const uint32_t ni = kmin & 3u;
+    int32_t next = ni == 0u ? refs.x : (ni == 1u ? refs.y : (ni == 2u ? refs.z : refs.w));
+    if (hx & (k0 != kmin)) stack[t.sp++] = refs.x;
+    if (hy & (k1 != kmin)) stack[t.sp++] = refs.y;
+    if (hz & (k2 != kmin)) stack[t.sp++] = refs.z;
+    if (hw & (k3 != kmin)) stack[t.sp++] = refs.w;
+    if (!any) next = stack[--t.sp];
+    if (next < 0 && next != kTravDone && t.leaf_left == 0) {  // a leaf and the slot is free: hold it, continue elsewhere
         trav_hold_leaf(t, next);
         next = stack[--t.sp];
     }

@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(kBlockThreads) pt_persistent_kernel(const __gr
 // waiting the warp leaves TRAVERSE, shades exactly those lanes (they get their bounce ray or the next camera
 // ray) and re-enters with the unfinished lanes resuming where they stopped — warp-level ray compaction without
 // moving any state between lanes, which the one-XORWOW-stream-per-pixel contract forbids.
-template <bool SPHERES, bool RTOW, bool COUNT, int MINB>
-__global__ void __launch_bounds__(kBlockThreads, MINB) pt_wavefront_kernel(const __grid_constant__ RenderParams p) {
+template <bool SPHERES, bool RTOW, bool COUNT, bool WIDE>
+__global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __grid_constant__ RenderParams p) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t total_items = work_total(p);
     const int refill_at = p.refill_at;
@@ -256,7 +256,10 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) pt_wavefront_kernel(const
             if (n_active == 0 || n_paths - n_active >= wait_for) break;
             if (__popc(m_node) >= __popc(m_prim)) {
                 for (int k = 0; k < node_burst; k++)
-                    if (tr.cur >= 0) trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
+                    if (tr.cur >= 0) {
+                        if (WIDE) trav_node_step4<COUNT>(p.scene, tr, stack, 0.001f, n_box);
+                        else trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
+                    }
             } else {
                 if (can_prim) trav_prim_step<SPHERES, COUNT>(p.scene, tr, stack, ro, rd, 0.001f, n_tri);
             }

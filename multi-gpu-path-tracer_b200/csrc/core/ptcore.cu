@@ -28,6 +28,7 @@ struct SceneBlob {
     uint8_t *pinned = nullptr;
     uint8_t *dev = nullptr;
     size_t bytes = 0;
+    size_t off_nodes4 = 0;
     size_t off_nodes = 0, off_prims = 0, off_shade = 0, off_mats = 0, off_texdesc = 0, off_texels = 0, off_lights = 0;
     int32_t n_prims = 0, n_lights = 0, n_nodes = 0;
     bool has_spheres = false, has_rtow = false;
@@ -70,6 +71,7 @@ struct ptcore {
     int refill_at = 24;
     int node_burst = 2;
     int min_blocks = 8;
+    int bvh_width = 4;
     uint32_t *ident_blocks = nullptr;
     uint32_t ident_blocks_n = 0;
 
@@ -150,8 +152,8 @@ cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaS
     } else {
         int occ = 0;
         cudaError_t e = h->kernel == PT_KERNEL_LOCKSTEP ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_persistent_kernel<S, R, C>, kBlockThreads, 0)
-                        : h->min_blocks >= 8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_wavefront_kernel<S, R, C, 8>, kBlockThreads, 0)
-                                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_wavefront_kernel<S, R, C, 6>, kBlockThreads, 0);
+                        : h->bvh_width == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_wavefront_kernel<S, R, C, true>, kBlockThreads, 0)
+                                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_wavefront_kernel<S, R, C, false>, kBlockThreads, 0);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
         if (h->blocks_per_sm > 0) occ = std::min(occ, h->blocks_per_sm);
@@ -159,8 +161,8 @@ cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaS
         uint32_t needed = (total + kBlockThreads - 1) / kBlockThreads;
         if (grid > needed) grid = needed;
         if (h->kernel == PT_KERNEL_LOCKSTEP) pt_persistent_kernel<S, R, C><<<grid, kBlockThreads, 0, stream>>>(rp);
-        else if (h->min_blocks >= 8) pt_wavefront_kernel<S, R, C, 8><<<grid, kBlockThreads, 0, stream>>>(rp);
-        else pt_wavefront_kernel<S, R, C, 6><<<grid, kBlockThreads, 0, stream>>>(rp);
+        else if (h->bvh_width == 4) pt_wavefront_kernel<S, R, C, true><<<grid, kBlockThreads, 0, stream>>>(rp);
+        else pt_wavefront_kernel<S, R, C, false><<<grid, kBlockThreads, 0, stream>>>(rp);
     }
     return cudaGetLastError();
 }
@@ -182,6 +184,7 @@ void fill_dev_scene(ptcore *h) {
     SceneBlob &b = h->blob;
     DevScene &d = h->dscene;
     d.nodes = reinterpret_cast<const float4 *>(b.dev + b.off_nodes);
+    d.nodes4 = reinterpret_cast<const float4 *>(b.dev + b.off_nodes4);
     d.prims = reinterpret_cast<const float4 *>(b.dev + b.off_prims);
     d.shade = reinterpret_cast<const float4 *>(b.dev + b.off_shade);
     d.mats = reinterpret_cast<const float4 *>(b.dev + b.off_mats);
@@ -378,6 +381,7 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
     if (texels >= 0xffffffffull) return fail(h, PT_ERR_UNSUPPORTED, "textures too large");
     size_t off = 0;
     nb.off_nodes = off; off = align_up(off + bvh.nodes.size() * sizeof(FlatNode), 256);
+    nb.off_nodes4 = off; off = align_up(off + bvh.nodes4.size() * sizeof(FlatNode4), 256);
     nb.off_prims = off; off = align_up(off + std::max<size_t>(1, (size_t)n_prims) * 48, 256);
     nb.off_shade = off; off = align_up(off + std::max<size_t>(1, (size_t)n_prims) * 32, 256);
     nb.off_mats = off; off = align_up(off + (size_t)sc->n_mats * 48, 256);
@@ -388,6 +392,8 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
     nb.host.assign(nb.bytes, 0);
 
     memcpy(nb.host.data() + nb.off_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(FlatNode));
+    memcpy(nb.host.data() + nb.off_nodes4, bvh.nodes4.data(), bvh.nodes4.size() * sizeof(FlatNode4));
+    if (bvh.stack4 > (uint32_t)kStackSize - 2) return fail(h, PT_ERR_UNSUPPORTED, "scene needs a deeper traversal stack than the device provides");
     float *prims = reinterpret_cast<float *>(nb.host.data() + nb.off_prims);
     float *shade = reinterpret_cast<float *>(nb.host.data() + nb.off_shade);
     for (int64_t k = 0; k < n_prims; k++) {
@@ -474,6 +480,8 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
     h->build_stats.bvh_nodes = (uint32_t)bvh.nodes.size();
     h->build_stats.bvh_leaves = bvh.n_leaves;
     h->build_stats.bvh_depth = bvh.depth;
+    h->build_stats.bvh4_nodes = (uint32_t)bvh.nodes4.size();
+    h->build_stats.bvh4_depth = bvh.depth4;
     h->build_stats.n_lights = (uint32_t)lights.size();
     h->build_stats.bvh_build_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     h->build_stats.sah_cost = bvh.sah_cost;
@@ -542,8 +550,12 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
             h->node_burst = (int)value;
             return PT_OK;
         case PT_OPT_MIN_BLOCKS:
-            if (value != 6 && value != 8) return fail(h, PT_ERR_INVALID_ARGUMENT, "min_blocks must be 6 or 8");
+            if (value != 8) return fail(h, PT_ERR_INVALID_ARGUMENT, "only the __launch_bounds__(128, 8) build is shipped");
             h->min_blocks = (int)value;
+            return PT_OK;
+        case PT_OPT_BVH_WIDTH:
+            if (value != 2 && value != 4) return fail(h, PT_ERR_INVALID_ARGUMENT, "bvh_width must be 2 or 4");
+            h->bvh_width = (int)value;
             return PT_OK;
         case PT_OPT_SLICE_SPP:
             if (value != 0) return fail(h, PT_ERR_UNSUPPORTED, "sample slicing is not implemented yet");
@@ -709,12 +721,15 @@ int pt_bvh_selftest(const PtSceneDesc *sc, int32_t leaf_max, PtStats *out, char 
     opt.leaf_max = leaf_max > 0 ? leaf_max : 4;
     BvhBuildResult bvh = build_bvh(pb, opt);
     const char *why = validate_bvh(bvh, pb);
+    if (why[0] == 0) why = validate_bvh4(bvh, pb);
     if (msg && msg_len) snprintf(msg, msg_len, "%s", why);
     if (out) {
         memset(out, 0, sizeof *out);
         out->bvh_nodes = (uint32_t)bvh.nodes.size();
         out->bvh_leaves = bvh.n_leaves;
         out->bvh_depth = bvh.depth;
+        out->bvh4_nodes = (uint32_t)bvh.nodes4.size();
+        out->bvh4_depth = bvh.depth4;
         out->bvh_build_ms = bvh.build_ms;
         out->sah_cost = bvh.sah_cost;
         out->scene_bytes = bvh.nodes.size() * sizeof(FlatNode);

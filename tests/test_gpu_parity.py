@@ -144,10 +144,10 @@ def test_direct_kernel_equals_persistent_kernel(tracer, duck, ptb):
     c, yc = render(tracer, duck, 120, 68, 6, 6, kernel=ptb.PT_KERNEL_LOCKSTEP, ptb=ptb)
     assert np.array_equal(a, c) and np.array_equal(ya, yc)
     # the step-scheduling knobs only change WHEN lanes run which step, never pixels
-    for refill_at, burst, minb in ((1, 1, 6), (5, 3, 8), (32, 2, 6), (20, 4, 8)):
+    for refill_at, burst, width in ((1, 1, 2), (5, 3, 4), (32, 2, 2), (20, 4, 4)):
         tracer.set_option(ptb.PT_OPT_REFILL_AT, refill_at)
         tracer.set_option(ptb.PT_OPT_NODE_BURST, burst)
-        tracer.set_option(ptb.PT_OPT_MIN_BLOCKS, minb)
+        tracer.set_option(ptb.PT_OPT_BVH_WIDTH, width)
         d, yd = render(tracer, duck, 120, 68, 6, 6, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
         assert np.array_equal(a, d) and np.array_equal(ya, yd)
 
