@@ -106,7 +106,7 @@ enum { /* ptcore_set_option keys */
     PT_OPT_REFILL_AT = 6,    /* wavefront kernel: finished lanes per warp that trigger a shade/refill pass (1..32, default 16) */
     PT_OPT_NODE_BURST = 7,   /* wavefront kernel: node steps per warp vote (1..4) */
     PT_OPT_MIN_BLOCKS = 8,   /* accepted for compatibility: only the __launch_bounds__(128, 8) (64-register) build is shipped */
-    PT_OPT_BVH_WIDTH = 9     /* wavefront kernel: walk the 2-wide (64 B nodes) or the collapsed 4-wide (128 B nodes) tree; default 4 */
+    PT_OPT_BVH_WIDTH = 9     /* wavefront kernel: walk the 2-wide (64 B nodes, default) or the collapsed 4-wide (128 B nodes) tree; 4-wide measured 20 % slower on cornell_duck */
 };
 enum {
     PT_KERNEL_PERSISTENT = 0, /* persistent-thread wavefront: per-lane pixel refill + warp-voted uniform traversal steps (default) */

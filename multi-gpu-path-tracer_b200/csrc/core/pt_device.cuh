@@ -426,15 +426,18 @@ __device__ __forceinline__ void trav_node_step4(const DevScene &sc, Trav &t, int
     const uint32_t k1 = hy ? ((__float_as_uint(tny) & ~3u) | 1u) : 0xffffffffu;
     const uint32_t k2 = hz ? ((__float_as_uint(tnz) & ~3u) | 2u) : 0xffffffffu;
     const uint32_t k3 = hw ? ((__float_as_uint(tnw) & ~3u) | 3u) : 0xffffffffu;
-    const uint32_t kmin = min(min(k0, k1), min(k2, k3));
-    const bool any = kmin != 0xffffffffu;
-    const uint32_t ni = kmin & 3u;
-    int32_t next = ni == 0u ? refs.x : (ni == 1u ? refs.y : (ni == 2u ? refs.z : refs.w));
-    if (hx & (k0 != kmin)) stack[t.sp++] = refs.x;
-    if (hy & (k1 != kmin)) stack[t.sp++] = refs.y;
-    if (hz & (k2 != kmin)) stack[t.sp++] = refs.z;
-    if (hw & (k3 != kmin)) stack[t.sp++] = refs.w;
-    if (!any) next = stack[--t.sp];
+    // sort the four keys (5-comparator network); misses (0xffffffff) end up last
+    const uint32_t a0 = min(k0, k1), a1 = max(k0, k1), a2 = min(k2, k3), a3 = max(k2, k3);
+    const uint32_t s0 = min(a0, a2), b1 = max(a0, a2), b2 = min(a1, a3), s3 = max(a1, a3);
+    const uint32_t s1 = min(b1, b2), s2 = max(b1, b2);
+#define PT_REF4(k) (((k) & 2u) ? (((k) & 1u) ? refs.w : refs.z) : (((k) & 1u) ? refs.y : refs.x))
+    // far children first, so that the nearer ones are popped first
+    if (s3 != 0xffffffffu) stack[t.sp++] = PT_REF4(s3);
+    if (s2 != 0xffffffffu) stack[t.sp++] = PT_REF4(s2);
+    if (s1 != 0xffffffffu) stack[t.sp++] = PT_REF4(s1);
+    int32_t next = PT_REF4(s0);
+#undef PT_REF4
+    if (s0 == 0xffffffffu) next = stack[--t.sp];
     if (next < 0 && next != kTravDone && t.leaf_left == 0) {  // a leaf and the slot is free: hold it, continue elsewhere
         trav_hold_leaf(t, next);
         next = stack[--t.sp];

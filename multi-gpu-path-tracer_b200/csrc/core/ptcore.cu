@@ -71,7 +71,7 @@ struct ptcore {
     int refill_at = 24;
     int node_burst = 2;
     int min_blocks = 8;
-    int bvh_width = 4;
+    int bvh_width = 2;
     uint32_t *ident_blocks = nullptr;
     uint32_t ident_blocks_n = 0;
 
