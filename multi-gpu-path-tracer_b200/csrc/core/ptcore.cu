@@ -31,7 +31,7 @@ struct SceneBlob {
     size_t off_nodes4 = 0;
     size_t off_nodes = 0, off_prims = 0, off_shade = 0, off_mats = 0, off_texdesc = 0, off_texels = 0, off_lights = 0;
     int32_t n_prims = 0, n_lights = 0, n_nodes = 0;
-    bool has_spheres = false, has_rtow = false;
+    bool has_spheres = false, has_rtow = false, has_nodes4 = false;
 };
 
 }  // namespace
@@ -168,6 +168,7 @@ cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaS
 }
 
 cudaError_t launch(ptcore *h, const RenderParams &rp, cudaStream_t stream) {
+    if (h->kernel == PT_KERNEL_PERSISTENT && h->bvh_width == 4 && !h->blob.has_nodes4) return cudaErrorNotSupported;  // upload the scene with PT_OPT_BVH_WIDTH = 4 first
     const bool direct = h->kernel == PT_KERNEL_DIRECT;
     const bool S = h->blob.has_spheres, R = h->blob.has_rtow, C = h->count_tests;
     if (!S && !R && !C) return launch_variant<false, false, false>(h, rp, direct, stream);
@@ -381,7 +382,10 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
     if (texels >= 0xffffffffull) return fail(h, PT_ERR_UNSUPPORTED, "textures too large");
     size_t off = 0;
     nb.off_nodes = off; off = align_up(off + bvh.nodes.size() * sizeof(FlatNode), 256);
-    nb.off_nodes4 = off; off = align_up(off + bvh.nodes4.size() * sizeof(FlatNode4), 256);
+    // the four-wide copy of the tree is only uploaded when it is selected or the scene is small: on large scenes it would
+    // just compete with the two-wide nodes for L2
+    nb.has_nodes4 = h->bvh_width == 4 || n_prims <= (1 << 18);
+    nb.off_nodes4 = off; off = align_up(off + (nb.has_nodes4 ? bvh.nodes4.size() : 1) * sizeof(FlatNode4), 256);
     nb.off_prims = off; off = align_up(off + std::max<size_t>(1, (size_t)n_prims) * 48, 256);
     nb.off_shade = off; off = align_up(off + std::max<size_t>(1, (size_t)n_prims) * 32, 256);
     nb.off_mats = off; off = align_up(off + (size_t)sc->n_mats * 48, 256);
@@ -392,8 +396,13 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
     nb.host.assign(nb.bytes, 0);
 
     memcpy(nb.host.data() + nb.off_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(FlatNode));
-    memcpy(nb.host.data() + nb.off_nodes4, bvh.nodes4.data(), bvh.nodes4.size() * sizeof(FlatNode4));
-    if (bvh.stack4 > (uint32_t)kStackSize - 2) return fail(h, PT_ERR_UNSUPPORTED, "scene needs a deeper traversal stack than the device provides");
+    if (nb.has_nodes4) {
+        memcpy(nb.host.data() + nb.off_nodes4, bvh.nodes4.data(), bvh.nodes4.size() * sizeof(FlatNode4));
+        if (bvh.stack4 > (uint32_t)kStackSize - 2) {
+            if (h->bvh_width == 4) return fail(h, PT_ERR_UNSUPPORTED, "scene needs a deeper traversal stack than the device provides for four-wide nodes");
+            nb.has_nodes4 = false;
+        }
+    }
     float *prims = reinterpret_cast<float *>(nb.host.data() + nb.off_prims);
     float *shade = reinterpret_cast<float *>(nb.host.data() + nb.off_shade);
     for (int64_t k = 0; k < n_prims; k++) {

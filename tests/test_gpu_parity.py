@@ -236,6 +236,20 @@ def test_displaced_mesh_config4_matches_oracle(tracer, oracle, duck, ptb):
     assert st["bvh_depth"] <= 48 and st["bvh_nodes"] > 4000
 
 
+def test_converged_render_matches_oracle(tracer, oracle, duck):
+    """North-star check 2: a converged render agrees within a stated RMSE.  2048 spp: by then ~95 % of the pixels have left
+    the oracle's stream at some sample (gate B), so this compares two independent Monte-Carlo estimates of the same
+    integrand (both carry the reference's 2x cosine-sampler bias).  Stated bound on the 8-bit image: RMSE <= 1.0 / 255."""
+    w, h, spp, depth = 96, 54, 2048, 8
+    rgb, _ = render(tracer, duck, w, h, spp, depth)
+    ref, _, _ = oracle.render(duck, w, h, spp, depth)
+    d = rgb.astype(np.float64) - ref.astype(np.float64)
+    rmse = float(np.sqrt((d ** 2).mean()))
+    print(dict(rmse=rmse, mean_abs=float(np.abs(d).mean()), max=float(np.abs(d).max()), identical=float((d == 0).all(axis=2).mean())))
+    assert rmse <= 1.0, rmse
+    assert abs(float(d.mean())) <= 0.1  # no bias between the two
+
+
 def test_tile_offsets_are_bottom_up(tracer, duck):
     import torch
     w, h = 64, 36

@@ -55,3 +55,22 @@ def test_oracle_no_emitter_scene_is_black_not_a_crash(oracle, box):
     rgb, _, st = oracle.render(box, 32, 18, 4, 8, camera=dict(look_from=(-250.0, 250.0, 250.0), front=(0.0, 0.0, -1.0)))
     assert not rgb.any()
     assert st["emitter_paths"] == 0
+
+
+def test_reference_cuda_and_host_builds_differ_by_the_stated_tolerance():
+    """Fixtures only: the reference's own CUDA renderer (B200) vs its own headers compiled for the host.  Same streams, same
+    code, different rounding — this is the cross-build variance that gate B of tests/test_gpu_parity.py has to absorb."""
+    ref_gpu_meta = json.loads((GOLD / "ref_gpu_images.json").read_text())["images"]
+    n = 0
+    for name, m in META.items():
+        if name not in ref_gpu_meta:
+            continue
+        cpu = np.array(Image.open(GOLD / f"ref_cpu_{name}.png").convert("RGB")).astype(np.int32)
+        gpu = np.array(Image.open(GOLD / f"ref_gpu_{name}.png").convert("RGB")).astype(np.int32)
+        d = np.abs(cpu - gpu)
+        frac1 = float((d.max(axis=2) <= 1).mean())
+        assert frac1 >= 1 - 1.5e-3 * m["spp"] - 0.005, (name, frac1)
+        assert d.mean() <= 0.5, (name, float(d.mean()))
+        assert frac1 < 1.0 or m["depth"] <= 3, name  # they do differ: bit-exactness across builds is not a property of the reference
+        n += 1
+    assert n >= 3
