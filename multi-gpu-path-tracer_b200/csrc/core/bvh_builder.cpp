@@ -7,7 +7,9 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <atomic>
 #include <numeric>
+#include <thread>
 
 namespace ptc {
 namespace {
@@ -40,7 +42,6 @@ struct Builder {
     std::vector<int32_t> order;
     std::vector<float> cent;  // 3 per prim
     std::vector<TmpNode> tmp;
-    std::vector<float> sweepArea;
     uint32_t maxDepth = 0;
 
     Builder(const std::vector<PrimBounds> &b, const BvhBuildOptions &o) : pb(b), opt(o) {}
@@ -74,7 +75,7 @@ struct Builder {
             if (count <= 64) {
                 // exact sweep over centroid-sorted order, all three axes
                 std::vector<int32_t> ids(order.begin() + first, order.begin() + first + count);
-                if ((int32_t)sweepArea.size() < count) sweepArea.resize((size_t)count);
+                std::vector<float> sweepArea((size_t)count);
                 for (int axis = 0; axis < 3; axis++) {
                     if (!(cbox.hi[axis] > cbox.lo[axis])) continue;
                     std::stable_sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) { return cent[(size_t)a * 3 + axis] < cent[(size_t)b * 3 + axis]; });
@@ -164,6 +165,38 @@ struct Builder {
         return m;
     }
 
+    struct Work { int32_t node; uint32_t depth; };
+
+    // Splits nodes[w.node] if the SAH says so; children are appended to `nodes` and pushed on `stack`.
+    void processNode(std::vector<TmpNode> &nodes, Work w, std::vector<Work> &stack, uint32_t &deepest) {
+        const int leafMax = std::max(1, std::min(opt.leaf_max, kMaxLeafPrims));
+        deepest = std::max(deepest, w.depth);
+        int32_t first = nodes[(size_t)w.node].first, count = nodes[(size_t)w.node].count;
+        if (count <= 1) return;
+        Box cbox;
+        Box box = rangeBox(first, count, &cbox);
+        bool mustSplit = count > leafMax;
+        // keep the tree shallow enough for the device stack: once deep, split by count
+        uint32_t remaining = 1;
+        while ((1u << remaining) * (uint32_t)leafMax < (uint32_t)count && remaining < 31) remaining++;
+        bool forceMedian = w.depth + remaining + 2 >= (uint32_t)kMaxTraversalDepth;
+        int32_t mid = findSplit(first, count, box, cbox, mustSplit, forceMedian);
+        if (mid < 0) return;
+        TmpNode l, r;
+        l.first = first; l.count = mid - first;
+        r.first = mid; r.count = first + count - mid;
+        l.box = rangeBox(l.first, l.count, nullptr);
+        r.box = rangeBox(r.first, r.count, nullptr);
+        int32_t li = (int32_t)nodes.size();
+        nodes.push_back(l);
+        int32_t ri = (int32_t)nodes.size();
+        nodes.push_back(r);
+        nodes[(size_t)w.node].left = li;
+        nodes[(size_t)w.node].right = ri;
+        stack.push_back({ri, w.depth + 1});
+        stack.push_back({li, w.depth + 1});
+    }
+
     void run() {
         const size_t n = pb.size();
         order.resize(n);
@@ -172,44 +205,68 @@ struct Builder {
         for (size_t i = 0; i < n; i++)
             for (int k = 0; k < 3; k++) cent[i * 3 + k] = 0.5f * (pb[i].lo[k] + pb[i].hi[k]);
         tmp.reserve(n ? 2 * n : 1);
-        struct Work { int32_t node; uint32_t depth; };
-        std::vector<Work> stack;
         TmpNode root;
         root.first = 0;
         root.count = (int32_t)n;
         Box cb;
         root.box = rangeBox(0, (int32_t)n, &cb);
         tmp.push_back(root);
+
+        // Phase 1 (serial): split the large nodes; subtrees of at most `grain` primitives are deferred.
+        // Phase 2 (threads): deferred subtrees own disjoint ranges of `order`, so they build independently into
+        // private node arrays that are appended afterwards.  The tree (and hence every image) does not depend on
+        // the thread count: only the numbering of the temporary nodes does, and flattening renumbers them.
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned nthreads = n >= 200000 ? std::min(hw, 32u) : 1u;
+        const int32_t grain = nthreads > 1 ? (int32_t)std::max<size_t>(4096, n / (8 * (size_t)nthreads)) : 0;
+        std::vector<Work> stack, deferred;
         stack.push_back({0, 1});
-        const int leafMax = std::max(1, std::min(opt.leaf_max, kMaxLeafPrims));
         while (!stack.empty()) {
             Work w = stack.back();
             stack.pop_back();
-            maxDepth = std::max(maxDepth, w.depth);
-            int32_t first = tmp[(size_t)w.node].first, count = tmp[(size_t)w.node].count;
-            if (count <= 1) continue;
-            Box cbox;
-            Box box = rangeBox(first, count, &cbox);
-            bool mustSplit = count > leafMax;
-            // keep the tree shallow enough for the device stack: once deep, split by count
-            uint32_t remaining = 1;
-            while ((1u << remaining) * (uint32_t)leafMax < (uint32_t)count && remaining < 31) remaining++;
-            bool forceMedian = w.depth + remaining + 2 >= (uint32_t)kMaxTraversalDepth;
-            int32_t mid = findSplit(first, count, box, cbox, mustSplit, forceMedian);
-            if (mid < 0) continue;
-            TmpNode l, r;
-            l.first = first; l.count = mid - first;
-            r.first = mid; r.count = first + count - mid;
-            l.box = rangeBox(l.first, l.count, nullptr);
-            r.box = rangeBox(r.first, r.count, nullptr);
-            int32_t li = (int32_t)tmp.size();
-            tmp.push_back(l);
-            int32_t ri = (int32_t)tmp.size();
-            tmp.push_back(r);
-            tmp[(size_t)w.node].left = li;
-            tmp[(size_t)w.node].right = ri;
-            stack.push_back({ri, w.depth + 1});
-            stack.push_back({li, w.depth + 1});
+            if (nthreads > 1 && tmp[(size_t)w.node].count <= grain) {
+                deferred.push_back(w);
+                continue;
+            }
+            processNode(tmp, w, stack, maxDepth);
+        }
+        if (deferred.empty()) return;
+        std::vector<std::vector<TmpNode>> local(deferred.size());
+        std::vector<uint32_t> localDepth(deferred.size(), 0);
+        std::atomic<size_t> nextJob{0};
+        auto worker = [&]() {
+            for (;;) {
+                size_t j = nextJob.fetch_add(1);
+                if (j >= deferred.size()) return;
+                std::vector<TmpNode> &nodes = local[j];
+                nodes.push_back(tmp[(size_t)deferred[j].node]);
+                std::vector<Work> st;
+                st.push_back({0, deferred[j].depth});
+                while (!st.empty()) {
+                    Work w = st.back();
+                    st.pop_back();
+                    processNode(nodes, w, st, localDepth[j]);
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(worker);
+        worker();
+        for (auto &t : pool) t.join();
+        for (size_t j = 0; j < deferred.size(); j++) {
+            maxDepth = std::max(maxDepth, localDepth[j]);
+            const std::vector<TmpNode> &nodes = local[j];
+            const int32_t base = (int32_t)tmp.size() - 1;  // local index k >= 1 becomes base + k
+            TmpNode &top = tmp[(size_t)deferred[j].node];
+            if (nodes[0].left >= 0) {
+                top.left = base + nodes[0].left;
+                top.right = base + nodes[0].right;
+            }
+            for (size_t k = 1; k < nodes.size(); k++) {
+                TmpNode c = nodes[k];
+                if (c.left >= 0) { c.left += base; c.right += base; }
+                tmp.push_back(c);
+            }
         }
     }
 };
