@@ -78,6 +78,13 @@ def build_tools(force: bool = False, verbose: bool = False) -> None:
     srcs = [CSRC / "tools" / "ptscene_tool.cpp", CSRC / "host" / "SceneLoader.cpp"]
     if force or _stale(tool, [*srcs, CSRC / "host" / "HostScene.h"]):
         _run([HOST_CXX, "-std=c++17", "-O2", "-ffp-contract=off", f"-I{CUDA_HOME}/include", *srcs, "-lz", "-o", tool], verbose)
+    test_src = CSRC / "host" / "host_api_test.cpp"
+    if test_src.exists():
+        exe = LIBDIR / "host_api_test"
+        deps = list((CSRC / "host").glob("*.h")) + [test_src, CSRC / "host" / "SceneLoader.cpp", ROOT / "include" / "ptcore.h"]
+        if force or _stale(exe, deps) or _stale(exe, [LIBDIR / "libptcore.so"]):
+            _run([HOST_CXX, "-std=c++17", "-O2", "-pthread", f"-I{CUDA_HOME}/include", f"-I{ROOT / 'include'}", test_src,
+                  f"-L{LIBDIR}", "-lptcore", f"-L{CUDA_HOME}/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{CUDA_HOME}/lib64", "-o", exe], verbose)
     cli_src = CSRC / "host" / "main.cpp"
     if cli_src.exists():
         cli = LIBDIR / "cuda_project"

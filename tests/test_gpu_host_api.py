@@ -63,3 +63,14 @@ def test_cli_show_tasks_draws_the_grid_like_the_reference(tmp_path, duck_file):
     ys, xs = np.nonzero(diff)
     assert set(np.unique(xs)) - set(range(158, 164)) == set() or set(np.unique(ys)) - set(range(148, 154)) == set() or True
     assert diff.sum() < 0.05 * diff.size
+
+
+def test_render_manager_runtime_api(duck_file):
+    """csrc/host/host_api_test.cpp: deferred setters, scheduler switches, GPU/stream changes, resolution change, borrowed camera,
+    scene reload, task overlay — what the reference's main loop and remote handlers do between frames."""
+    exe = ROOT / "multi-gpu-path-tracer_b200" / "_lib" / "host_api_test"
+    if not exe.exists():
+        pytest.skip("host_api_test not built")
+    r = subprocess.run([str(exe), str(duck_file)], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
