@@ -67,7 +67,6 @@ struct ptcore {
     bool count_tests = false;
     int leaf_max = 4;
     int blocks_per_sm = 0;
-    int slice_spp = 0;
     int refill_at = 24;
     int node_burst = 2;
     int min_blocks = 8;
@@ -565,10 +564,6 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
         case PT_OPT_BVH_WIDTH:
             if (value != 2 && value != 4) return fail(h, PT_ERR_INVALID_ARGUMENT, "bvh_width must be 2 or 4");
             h->bvh_width = (int)value;
-            return PT_OK;
-        case PT_OPT_SLICE_SPP:
-            if (value != 0) return fail(h, PT_ERR_UNSUPPORTED, "sample slicing is not implemented yet");
-            h->slice_spp = 0;
             return PT_OK;
         default: return fail(h, PT_ERR_UNSUPPORTED, "unknown option key");
     }
