@@ -171,7 +171,7 @@ def run_reference_arm(args, rank):
     vals, secs = [], []
     last = None
     for _ in range(args.steps):
-        last = cpu_reference_sample(threads)
+        last = cpu_reference_sample(threads, **({"rect": (880, 500, 160, 80), "spp": 1} if args.ref_sample == "small" else {}))
         vals.append(last["value"]); secs.append(last["seconds"])
     value = sum(last["samples"] for _ in vals) / sum(secs) / 1e6
     line = {"impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -205,6 +205,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-sample", default="default", choices=["default", "small"], help="--impl reference: size of the bounded CPU sample (small: for tests)")
     ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
                     help="config2 (default, the bench line): 1080p/1024 spp; config5: 3840x2160/4096 spp, the strong-scaling case of BASELINE.json (a parity-test case, not the bench line)")
     args = ap.parse_args()
