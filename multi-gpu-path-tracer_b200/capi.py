@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import gzip
+import os
 import struct
 from dataclasses import dataclass, field
 from pathlib import Path
@@ -175,7 +176,7 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path else LIB_PATH
+    p = Path(path) if path else Path(os.environ.get("PTB200_LIBPTCORE", LIB_PATH))  # the variable: A/B builds of the same ABI
     if not p.exists():
         raise FileNotFoundError(f"{p} is missing — run __graft_entry__.build() (nvcc, sm_100a); there is no fallback path")
     lib = C.CDLL(str(p))

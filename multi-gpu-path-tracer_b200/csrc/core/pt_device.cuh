@@ -11,6 +11,9 @@
 #include <float.h>
 #include <stdint.h>
 
+// per-hit data (shading frames, texture coordinates, texels) is read once per ray: through L2 only, so that it does not
+// push BVH nodes and triangles out of L1
+#define PT_LDSHADE(p) __ldcg(p)
 namespace ptc {
 
 #ifndef PT_M_PI
@@ -36,7 +39,11 @@ struct DevScene {
     const float4 *mats;    // 3 per material : (type, base.rgb) (emis.rgb, base_tex) (emis_tex, fuzz, ior, -)
     const TexDesc *texs;
     const float4 *texels;  // (r,g,b,-) already scaled by 1/255 exactly as Texture.h:45-46 does
-    const float4 *lights;  // 3 per light triangle: (v0.xyz, area) (v1.xyz, -) (v2.xyz, -), scene order
+    const float4 *frames;  // 4 per primitive, written once per upload by pt_frames_kernel with the very device functions shade() would
+                           //   call per hit (hit_record.normal and the onb of cosine_pdf are per-triangle constants):
+                           //   (normal.xyz, material index) (w.xyz, kind) (u.xyz, v.x) (v.yz, -, -); spheres: only .w of the first two
+    const float4 *lights;  // 4 per light triangle: (v0.xyz, area) (v1.xyz, n.x) (v2.xyz, n.y) (n.z, -, -, -), scene order;
+                           //   n = normalize(cross(v1 - v0, v2 - v0)) by pt_frames_kernel (triangle.h:36)
     int32_t n_lights;
     int32_t n_prims;
     double light_pick_scale;  // (n_lights - 1) + 0.999999, hitable_list.h:24
@@ -331,6 +338,9 @@ struct Trav {
     Hit best;
 };
 
+__device__ __forceinline__ void trav_push(Trav &t, int32_t *stack, int32_t x) { stack[t.sp++] = x; }
+__device__ __forceinline__ int32_t trav_pop(Trav &t, int32_t *stack) { return stack[--t.sp]; }
+
 __device__ __forceinline__ void trav_idle(Trav &t) {
     t.cur = kTravDone;
     t.leaf_left = 0;
@@ -386,15 +396,15 @@ __device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, int3
     const bool holdNear = any & (nearRef < 0) & (t.leaf_left == 0);  // reached a leaf and the slot is free: hold it
     const bool needPush = both & !holdNear;
     const bool needPop = !any | (holdNear & !both);
+    int32_t next = holdNear ? farRef : nearRef;
     if (needPush) stack[t.sp] = farRef;
     t.sp += needPush ? 1 : 0;
     t.sp -= needPop ? 1 : 0;
-    int32_t next = holdNear ? farRef : nearRef;
     if (needPop) next = stack[t.sp];
     if (holdNear) trav_hold_leaf(t, nearRef);
     if (next < 0 && next != kTravDone && t.leaf_left == 0) {  // the successor is itself a leaf and the slot is (still) free
         trav_hold_leaf(t, next);
-        next = stack[--t.sp];
+        next = trav_pop(t, stack);
     }
     t.cur = next;
 }
@@ -432,15 +442,15 @@ __device__ __forceinline__ void trav_node_step4(const DevScene &sc, Trav &t, int
     const uint32_t s1 = min(b1, b2), s2 = max(b1, b2);
 #define PT_REF4(k) (((k) & 2u) ? (((k) & 1u) ? refs.w : refs.z) : (((k) & 1u) ? refs.y : refs.x))
     // far children first, so that the nearer ones are popped first
-    if (s3 != 0xffffffffu) stack[t.sp++] = PT_REF4(s3);
-    if (s2 != 0xffffffffu) stack[t.sp++] = PT_REF4(s2);
-    if (s1 != 0xffffffffu) stack[t.sp++] = PT_REF4(s1);
+    if (s3 != 0xffffffffu) trav_push(t, stack, PT_REF4(s3));
+    if (s2 != 0xffffffffu) trav_push(t, stack, PT_REF4(s2));
+    if (s1 != 0xffffffffu) trav_push(t, stack, PT_REF4(s1));
     int32_t next = PT_REF4(s0);
 #undef PT_REF4
-    if (s0 == 0xffffffffu) next = stack[--t.sp];
+    if (s0 == 0xffffffffu) next = trav_pop(t, stack);
     if (next < 0 && next != kTravDone && t.leaf_left == 0) {  // a leaf and the slot is free: hold it, continue elsewhere
         trav_hold_leaf(t, next);
-        next = stack[--t.sp];
+        next = trav_pop(t, stack);
     }
     t.cur = next;
 }
@@ -473,7 +483,7 @@ __device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, int3
     t.leaf_left -= 1;
     if (t.leaf_left == 0 && t.cur < 0 && t.cur != kTravDone) {  // a second leaf was waiting in `cur`
         trav_hold_leaf(t, t.cur);
-        t.cur = stack[--t.sp];
+        t.cur = trav_pop(t, stack);
     }
 }
 
@@ -500,8 +510,10 @@ __device__ __forceinline__ float3 random_cosine_direction(Rng &rng) {  // helper
     float r2 = rng_uniform(rng);
     float z = sqrtf(1 - r2);
     float phi = (float)(2 * PT_M_PI * r1);
-    float x = cosf(phi) * 2 * sqrtf(r2);
-    float y = sinf(phi) * 2 * sqrtf(r2);
+    float sn, cs;
+    sincosf(phi, &sn, &cs);  // one argument reduction; bit-identical to cosf(phi) / sinf(phi) (gate A, tests/test_gpu_parity.py)
+    float x = cs * 2 * sqrtf(r2);
+    float y = sn * 2 * sqrtf(r2);
     return f3(x, y, z);
 }
 
@@ -526,17 +538,18 @@ __device__ __forceinline__ float3 texture_value(const DevScene &sc, int tex, flo
     int y = j < 0 ? 0 : (j < td.height ? j : td.height - 1);
     y = td.height - y;
     if (y >= td.height) y = td.height - 1;  // the reference reads one row past the end here; defined as the last row
-    const float4 t = __ldg(&sc.texels[td.offset + (uint32_t)y * (uint32_t)td.width + (uint32_t)x]);
+    const float4 t = PT_LDSHADE(&sc.texels[td.offset + (uint32_t)y * (uint32_t)td.width + (uint32_t)x]);
     return f3(t.x, t.y, t.z);
 }
 
 // triangle::pdf_value (triangle.h:32-40) for one light triangle stored as v0/v1/v2/area
-__device__ __forceinline__ float light_pdf_value(float3 v0, float3 v1, float3 v2, float area, float3 o, float3 dir) {
+__device__ __forceinline__ float3 light_normal(float3 v0, float3 v1, float3 v2) { return normalize(cross(v1 - v0, v2 - v0)); }
+__device__ __forceinline__ float light_pdf_value(const float4 *lt, float3 v0, float3 v1, float3 v2, float nx, float ny, float area, float3 o, float3 dir) {
     float3 e1 = v1 - v0;
     float3 e2 = v2 - v0;
     float t, u, v;
     if (!triangle_test(v0, e1, e2, o, dir, 0.001f, FLT_MAX, t, u, v)) return 0;
-    float3 normal = normalize(cross(e1, e2));
+    float3 normal = f3(nx, ny, __ldg(&lt[3]).x);
     float distance_squared = t * t * dot(dir, dir);
     float cosine = fabsf(dot(dir, normal) / length(dir));
     return distance_squared / (cosine * area);
@@ -559,6 +572,15 @@ __device__ __forceinline__ float schlick(float cosine, float ref_idx) {  // mate
     float x = 1 - cosine;
     float x2 = x * x, x4 = x2 * x2, x5 = x4 * x;
     return r0 + (1 - r0) * x5;
+}
+
+// x / y, bit for bit, for a numerator that is often exactly zero (scattering_pdf == 0 below the surface): the compiler's IEEE
+// division sends a zero numerator down its out-of-line slow path (~35 instructions for a handful of lanes); 0 / y is (+-)0
+// for every y that is neither 0 nor NaN.
+__device__ __forceinline__ float div_often_zero(float x, float y) {
+    const bool z = (x == 0.0f) & (fabsf(y) > 0.0f);
+    const float q = (z ? 1.0f : x) / y;
+    return z ? __int_as_float((__float_as_int(x) ^ __float_as_int(y)) & (int)0x80000000) : q;
 }
 
 // camera.h:95-97
@@ -606,24 +628,18 @@ __device__ __forceinline__ bool shade(const DevScene &sc, const Hit &h, float3 &
         contrib = f3(0.0f, 0.0f, 0.0f) * att;  // camera.h:79,109: background (0,0,0) * attenuation (NaN/inf propagate as in the reference)
         return false;
     }
-    const float4 q0 = __ldg(&sc.prims[h.prim * 3 + 0]);
-    const float4 q1 = __ldg(&sc.prims[h.prim * 3 + 1]);
-    const float4 q2 = __ldg(&sc.prims[h.prim * 3 + 2]);
-    const float4 s0 = __ldg(&sc.shade[h.prim * 2 + 0]);
-    const float4 s1 = __ldg(&sc.shade[h.prim * 2 + 1]);
-    const int mat = __float_as_int(s1.z);
+    const float4 f0 = PT_LDSHADE(&sc.frames[h.prim * 4 + 0]);
+    const float4 f1 = PT_LDSHADE(&sc.frames[h.prim * 4 + 1]);
+    const int mat = __float_as_int(f0.w);
+    const bool sphere = SPHERES && __float_as_int(f1.w) == 1;
 
     const float3 p = o + h.t * d;  // ray.h:19
     float3 normal;
-    float tu, tv;
-    if (SPHERES && __float_as_int(q2.z) == 1) {
+    if (sphere) {
+        const float4 q0 = __ldg(&sc.prims[h.prim * 3 + 0]);
         normal = (p - f3(q0.x, q0.y, q0.z)) / q0.w;  // sphere.h:33
-        tu = tv = 0.f;
     } else {
-        const float3 e1 = f3(q0.w, q1.x, q1.y), e2 = f3(q1.z, q1.w, q2.x);
-        normal = normalize(cross(e1, e2));  // triangle.h:103 — geometric, never flipped towards the ray
-        tu = (1 - h.u - h.v) * s0.x + h.u * s0.z + h.v * s1.x;  // triangle.h:106-107
-        tv = (1 - h.u - h.v) * s0.y + h.u * s0.w + h.v * s1.y;
+        normal = f3(f0.x, f0.y, f0.z);  // triangle.h:103 normalize(cross(e1, e2)) — geometric, never flipped towards the ray
     }
 
     const float4 m0 = __ldg(&sc.mats[mat * 3 + 0]);
@@ -634,6 +650,13 @@ __device__ __forceinline__ bool shade(const DevScene &sc, const Hit &h, float3 &
     const float3 emis = f3(m1.x, m1.y, m1.z);
     const int base_tex = __float_as_int(m1.w);
     const int emis_tex = __float_as_int(m2.x);
+    float tu = 0.f, tv = 0.f;
+    if (!sphere && (base_tex >= 0 || emis_tex >= 0)) {
+        const float4 s0 = PT_LDSHADE(&sc.shade[h.prim * 2 + 0]);
+        const float4 s1 = PT_LDSHADE(&sc.shade[h.prim * 2 + 1]);
+        tu = (1 - h.u - h.v) * s0.x + h.u * s0.z + h.v * s1.x;  // triangle.h:106-107
+        tv = (1 - h.u - h.v) * s0.y + h.u * s0.w + h.v * s1.y;
+    }
 
     if (!RTOW || type == 4 /* PT_MAT_UNIVERSAL */) {
         // UniversalMaterial::emitted / scatter, material.h:52-86
@@ -651,32 +674,41 @@ __device__ __forceinline__ bool shade(const DevScene &sc, const Hit &h, float3 &
         if (base_tex >= 0) attenuation = attenuation * texture_value(sc, base_tex, tu, tv);  // material.h:71-75
 
         // camera.h:62-66: mixture_pdf(light list, cosine).generate / .value — pdf.h:57-75
-        const Onb uvw = make_onb(normal);
+        // the onb of cosine_pdf (pdf.h:16, onb.h:8-13): per-triangle constants from the frames table; built here for spheres
+        Onb uvw;
+        if (sphere) uvw = make_onb(normal);
+        else uvw.w = f3(f1.x, f1.y, f1.z);
         float3 dir;
         const bool have_lights = sc.n_lights > 0;
         const float pick = rng_uniform(rng);
         if (have_lights && pick < 0.5f) {
             // hitable_list::random (hitable_list.h:23-26) -> triangle::random (triangle.h:41-47)
             int index = (int)truncf((float)(rng_uniform(rng) * sc.light_pick_scale));
-            const float4 l0 = __ldg(&sc.lights[index * 3 + 0]);
-            const float4 l1 = __ldg(&sc.lights[index * 3 + 1]);
-            const float4 l2 = __ldg(&sc.lights[index * 3 + 2]);
+            const float4 l0 = __ldg(&sc.lights[index * 4 + 0]);
+            const float4 l1 = __ldg(&sc.lights[index * 4 + 1]);
+            const float4 l2 = __ldg(&sc.lights[index * 4 + 2]);
             float r1 = rng_uniform(rng);
             float r2 = rng_uniform(rng);
             float sqrt_r1 = sqrtf(r1);
             float3 random_point = (1 - sqrt_r1) * f3(l0.x, l0.y, l0.z) + (sqrt_r1 * (1 - r2)) * f3(l1.x, l1.y, l1.z) + (sqrt_r1 * r2) * f3(l2.x, l2.y, l2.z);
             dir = random_point - p;
         } else {
+            if (!sphere) {
+                const float4 f2 = PT_LDSHADE(&sc.frames[h.prim * 4 + 2]);
+                const float4 f3_ = PT_LDSHADE(&sc.frames[h.prim * 4 + 3]);
+                uvw.u = f3(f2.x, f2.y, f2.z);
+                uvw.v = f3(f2.w, f3_.x, f3_.y);
+            }
             dir = onb_local(uvw, random_cosine_direction(rng));  // cosine_pdf::generate, pdf.h:23-25
         }
         // hitable_list::pdf_value, hitable_list.h:16-22
         float light_pdf = 0.0f;
         for (int i = 0; i < sc.n_lights; i++) {
-            const float4 l0 = __ldg(&sc.lights[i * 3 + 0]);
-            const float4 l1 = __ldg(&sc.lights[i * 3 + 1]);
-            const float4 l2 = __ldg(&sc.lights[i * 3 + 2]);
+            const float4 l0 = __ldg(&sc.lights[i * 4 + 0]);
+            const float4 l1 = __ldg(&sc.lights[i * 4 + 1]);
+            const float4 l2 = __ldg(&sc.lights[i * 4 + 2]);
             if (COUNT) n_light += 1;
-            light_pdf += sc.light_weight * light_pdf_value(f3(l0.x, l0.y, l0.z), f3(l1.x, l1.y, l1.z), f3(l2.x, l2.y, l2.z), l0.w, p, dir);
+            light_pdf += sc.light_weight * light_pdf_value(&sc.lights[i * 4], f3(l0.x, l0.y, l0.z), f3(l1.x, l1.y, l1.z), f3(l2.x, l2.y, l2.z), l1.w, l2.w, l0.w, p, dir);
         }
         // cosine_pdf::value, pdf.h:19-22 (w = normalize(normal) once more, as onb's constructor does)
         const float3 ndir = normalize(dir);
@@ -686,7 +718,8 @@ __device__ __forceinline__ bool shade(const DevScene &sc, const Hit &h, float3 &
         // UniversalMaterial::scattering_pdf, material.h:88-91
         float cosine2 = dot(normal, ndir);
         float scattering_pdf = cosine2 < 0 ? 0 : div_pi(cosine2);
-        att = att * (attenuation * scattering_pdf / pdf_value);  // camera.h:69
+        const float3 num = attenuation * scattering_pdf;
+        att = att * f3(div_often_zero(num.x, pdf_value), div_often_zero(num.y, pdf_value), div_often_zero(num.z, pdf_value));  // camera.h:69
         o = p;
         d = dir;
         return true;

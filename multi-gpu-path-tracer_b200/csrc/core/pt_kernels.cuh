@@ -255,11 +255,16 @@ __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __
             const int n_active = __popc(m_node | m_prim);
             if (n_active == 0 || n_paths - n_active >= wait_for) break;
             if (__popc(m_node) >= __popc(m_prim)) {
-                for (int k = 0; k < node_burst; k++)
-                    if (tr.cur >= 0) {
-                        if (WIDE) trav_node_step4<COUNT>(p.scene, tr, stack, 0.001f, n_box);
-                        else trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
-                    }
+                if (!WIDE && node_burst == 2) {  // the default, without the loop bookkeeping
+                    if (can_node) trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
+                    if (tr.cur >= 0) trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
+                } else {
+                    for (int k = 0; k < node_burst; k++)
+                        if (tr.cur >= 0) {
+                            if (WIDE) trav_node_step4<COUNT>(p.scene, tr, stack, 0.001f, n_box);
+                            else trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
+                        }
+                }
             } else {
                 if (can_prim) trav_prim_step<SPHERES, COUNT>(p.scene, tr, stack, ro, rd, 0.001f, n_tri);
             }
@@ -301,6 +306,30 @@ __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __
             atomicAdd(&p.counters->tri_tests, acc_tri);
             atomicAdd(&p.counters->light_tests, acc_light);
         }
+    }
+}
+
+// Once per scene upload: the shading frame of every triangle (hit_record.normal, triangle.h:103, and the onb that
+// cosine_pdf builds from it, onb.h:8-13) and the normal of every light triangle (triangle.h:36), through the same device
+// functions a per-hit evaluation would inline, so shade() loads what the reference recomputes at every bounce.
+__global__ void pt_frames_kernel(const DevScene sc, float4 *frames, float4 *lights) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < sc.n_prims && __float_as_int(frames[k * 4 + 1].w) == 0) {
+        const float4 q0 = sc.prims[k * 3 + 0], q1 = sc.prims[k * 3 + 1], q2 = sc.prims[k * 3 + 2];
+        const float3 e1 = f3(q0.w, q1.x, q1.y), e2 = f3(q1.z, q1.w, q2.x);
+        const float3 normal = normalize(cross(e1, e2));
+        const Onb o = make_onb(normal);
+        frames[k * 4 + 0] = make_float4(normal.x, normal.y, normal.z, frames[k * 4 + 0].w);
+        frames[k * 4 + 1] = make_float4(o.w.x, o.w.y, o.w.z, frames[k * 4 + 1].w);
+        frames[k * 4 + 2] = make_float4(o.u.x, o.u.y, o.u.z, o.v.x);
+        frames[k * 4 + 3] = make_float4(o.v.y, o.v.z, 0.f, 0.f);
+    }
+    if (k < sc.n_lights) {
+        const float4 l0 = lights[k * 4 + 0], l1 = lights[k * 4 + 1], l2 = lights[k * 4 + 2];
+        const float3 n = light_normal(f3(l0.x, l0.y, l0.z), f3(l1.x, l1.y, l1.z), f3(l2.x, l2.y, l2.z));
+        lights[k * 4 + 1].w = n.x;
+        lights[k * 4 + 2].w = n.y;
+        lights[k * 4 + 3] = make_float4(n.z, 0.f, 0.f, 0.f);
     }
 }
 

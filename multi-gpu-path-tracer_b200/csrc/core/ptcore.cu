@@ -29,7 +29,7 @@ struct SceneBlob {
     uint8_t *dev = nullptr;
     size_t bytes = 0;
     size_t off_nodes4 = 0;
-    size_t off_nodes = 0, off_prims = 0, off_shade = 0, off_mats = 0, off_texdesc = 0, off_texels = 0, off_lights = 0;
+    size_t off_nodes = 0, off_prims = 0, off_shade = 0, off_frames = 0, off_mats = 0, off_texdesc = 0, off_texels = 0, off_lights = 0;
     int32_t n_prims = 0, n_lights = 0, n_nodes = 0;
     bool has_spheres = false, has_rtow = false, has_nodes4 = false;
 };
@@ -187,6 +187,7 @@ void fill_dev_scene(ptcore *h) {
     d.nodes4 = reinterpret_cast<const float4 *>(b.dev + b.off_nodes4);
     d.prims = reinterpret_cast<const float4 *>(b.dev + b.off_prims);
     d.shade = reinterpret_cast<const float4 *>(b.dev + b.off_shade);
+    d.frames = reinterpret_cast<const float4 *>(b.dev + b.off_frames);
     d.mats = reinterpret_cast<const float4 *>(b.dev + b.off_mats);
     d.texs = reinterpret_cast<const TexDesc *>(b.dev + b.off_texdesc);
     d.texels = reinterpret_cast<const float4 *>(b.dev + b.off_texels);
@@ -387,10 +388,11 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
     nb.off_nodes4 = off; off = align_up(off + (nb.has_nodes4 ? bvh.nodes4.size() : 1) * sizeof(FlatNode4), 256);
     nb.off_prims = off; off = align_up(off + std::max<size_t>(1, (size_t)n_prims) * 48, 256);
     nb.off_shade = off; off = align_up(off + std::max<size_t>(1, (size_t)n_prims) * 32, 256);
+    nb.off_frames = off; off = align_up(off + std::max<size_t>(1, (size_t)n_prims) * 64, 256);
     nb.off_mats = off; off = align_up(off + (size_t)sc->n_mats * 48, 256);
     nb.off_texdesc = off; off = align_up(off + std::max<size_t>(1, (size_t)sc->n_tex) * sizeof(TexDesc), 256);
     nb.off_texels = off; off = align_up(off + std::max<size_t>(1, texels) * 16, 256);
-    nb.off_lights = off; off = align_up(off + std::max<size_t>(1, lights.size()) * 48, 256);
+    nb.off_lights = off; off = align_up(off + std::max<size_t>(1, lights.size()) * 64, 256);
     nb.bytes = off;
     nb.host.assign(nb.bytes, 0);
 
@@ -404,10 +406,12 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
     }
     float *prims = reinterpret_cast<float *>(nb.host.data() + nb.off_prims);
     float *shade = reinterpret_cast<float *>(nb.host.data() + nb.off_shade);
+    float *frames = reinterpret_cast<float *>(nb.host.data() + nb.off_frames);
     for (int64_t k = 0; k < n_prims; k++) {
         int32_t id = bvh.prim_order[(size_t)k];
         float *q = prims + k * 12;
         float *s = shade + k * 8;
+        float *f = frames + k * 16;  // the vectors are filled in on the device (pt_frames_kernel)
         if (id < sc->n_tris) {
             const float *p = sc->tri_pos + (size_t)id * 9;
             q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
@@ -416,12 +420,16 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
             q[9] = 0.f; q[10] = as_float(0); q[11] = 0.f;
             if (sc->tri_uv) memcpy(s, sc->tri_uv + (size_t)id * 6, 6 * sizeof(float));
             s[6] = as_float(sc->tri_mat[id]);
+            f[3] = s[6];
+            f[7] = as_float(0);
         } else {
             const int32_t si = id - sc->n_tris;
             const float *sp = sc->sph + (size_t)si * 4;
             q[0] = sp[0]; q[1] = sp[1]; q[2] = sp[2]; q[3] = sp[3];
             q[10] = as_float(1);
             s[6] = as_float(sc->sph_mat[si]);
+            f[3] = s[6];
+            f[7] = as_float(1);
             nb.has_spheres = true;
         }
         s[7] = as_float(id);
@@ -459,7 +467,7 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
     float *lt = reinterpret_cast<float *>(nb.host.data() + nb.off_lights);
     for (size_t i = 0; i < lights.size(); i++) {
         const float *p = sc->tri_pos + (size_t)lights[i] * 9;
-        float *q = lt + i * 12;
+        float *q = lt + i * 16;
         q[0] = p[0]; q[1] = p[1]; q[2] = p[2]; q[3] = triangle_area_host(p);
         q[4] = p[3]; q[5] = p[4]; q[6] = p[5]; q[7] = 0.f;
         q[8] = p[6]; q[9] = p[7]; q[10] = p[8]; q[11] = 0.f;
@@ -483,6 +491,18 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
     nb.host.shrink_to_fit();
     h->blob = std::move(nb);
     fill_dev_scene(h);
+    // per-primitive shading frames and light normals, evaluated on the device (rsqrtf is not reproducible on the host) and
+    // copied back into the pinned image of the blob so that ptcore_reupload_scene restores them too
+    {
+        SceneBlob &b = h->blob;
+        const int n = std::max(b.n_prims, b.n_lights);
+        if (n > 0) {
+            pt_frames_kernel<<<(n + 255) / 256, 256>>>(h->dscene, reinterpret_cast<float4 *>(b.dev + b.off_frames), reinterpret_cast<float4 *>(b.dev + b.off_lights));
+            PT_CUDA(h, cudaGetLastError());
+            PT_CUDA(h, cudaMemcpy(b.pinned + b.off_frames, b.dev + b.off_frames, (size_t)std::max(1, b.n_prims) * 64, cudaMemcpyDeviceToHost));
+            PT_CUDA(h, cudaMemcpy(b.pinned + b.off_lights, b.dev + b.off_lights, (size_t)std::max(1, b.n_lights) * 64, cudaMemcpyDeviceToHost));
+        }
+    }
     h->have_scene = true;
 
     h->build_stats.bvh_nodes = (uint32_t)bvh.nodes.size();
