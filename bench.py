@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--node-burst", type=int, default=0)
     ap.add_argument("--min-blocks", type=int, default=0)
     ap.add_argument("--bvh-width", type=int, default=0)
+    ap.add_argument("--node-format", type=int, default=0, help="1 = 64-byte float nodes, 2 = 32-byte quantised nodes (0 = library default)")
     ap.add_argument("--sched", default="lpt", choices=["lpt", "tiles"], help="lpt: pilot pass + cost-sorted 8x4 blocks dealt round-robin to the ranks; tiles: dynamic tile claims")
     ap.add_argument("--pilot-spp", type=int, default=4)
     ap.add_argument("--emulate-world", type=int, default=0, help="experiments: render only rank 0's share of an N-rank frame on one GPU")
@@ -255,6 +256,8 @@ def main():
         pt.set_option(ptb200.PT_OPT_MIN_BLOCKS, args.min_blocks)
     if args.bvh_width:
         pt.set_option(ptb200.PT_OPT_BVH_WIDTH, args.bvh_width)
+    if args.node_format:
+        pt.set_option(ptb200.PT_OPT_NODE_FORMAT, args.node_format)
 
     tw, th = (int(x) for x in args.tile.split("x"))
     if world == 1:

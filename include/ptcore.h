@@ -106,7 +106,13 @@ enum { /* ptcore_set_option keys */
     PT_OPT_REFILL_AT = 6,    /* wavefront kernel: finished lanes per warp that trigger a shade/refill pass (1..32, default 16) */
     PT_OPT_NODE_BURST = 7,   /* wavefront kernel: node steps per warp vote (1..4) */
     PT_OPT_MIN_BLOCKS = 8,   /* accepted for compatibility: only the __launch_bounds__(128, 8) (64-register) build is shipped */
-    PT_OPT_BVH_WIDTH = 9     /* wavefront kernel: walk the 2-wide (64 B nodes, default) or the collapsed 4-wide (128 B nodes) tree; 4-wide measured 20 % slower on cornell_duck */
+    PT_OPT_BVH_WIDTH = 9,    /* wavefront kernel: walk the 2-wide (64 B nodes, default) or the collapsed 4-wide (128 B nodes) tree; 4-wide measured 20 % slower on cornell_duck */
+    PT_OPT_NODE_FORMAT = 10  /* wavefront kernel, 2-wide tree: PT_NODES_* */
+};
+enum {
+    PT_NODES_AUTO = 0,       /* default: quantised when PtStats.quant_inflation <= 1.3, else full */
+    PT_NODES_FULL = 1,       /* 64-byte nodes, float planes */
+    PT_NODES_QUANTISED = 2   /* 32-byte nodes, 15-bit planes on a scene-wide grid, rounded outwards (same pixels; smaller working set, looser boxes) */
 };
 enum {
     PT_KERNEL_PERSISTENT = 0, /* persistent-thread wavefront: per-lane pixel refill + warp-voted uniform traversal steps (default) */
@@ -126,6 +132,7 @@ typedef struct PtStats {
     double sah_cost;
     uint64_t scene_bytes; /* size of the compiled device blob */
     uint32_t bvh4_nodes, bvh4_depth; /* the collapsed four-wide tree */
+    double quant_inflation; /* mean over the leaves of (box area in the quantised nodes / in the float nodes); 1 = nothing lost */
 } PtStats;
 
 /* ---- lifetime (DevicePathTracer ctor/dtor, src/DevicePathTracer.h:169-192,372-377) ---- */

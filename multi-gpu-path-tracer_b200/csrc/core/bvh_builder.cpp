@@ -431,6 +431,93 @@ BvhBuildResult build_bvh(const std::vector<PrimBounds> &bounds, const BvhBuildOp
     return out;
 }
 
+QuantGrid quantise_nodes(const std::vector<FlatNode> &nodes, std::vector<QuantNode> &out) {
+    QuantGrid g{};
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (const FlatNode &n : nodes)
+        for (int side = 0; side < 2; side++) {
+            const float b[3][2] = {{n.bx[side * 2], n.bx[side * 2 + 1]}, {n.by[side * 2], n.by[side * 2 + 1]}, {n.bz[side * 2], n.bz[side * 2 + 1]}};
+            if (!(b[0][0] <= b[0][1])) continue;  // absent child
+            for (int k = 0; k < 3; k++) {
+                if (std::isfinite(b[k][0])) lo[k] = std::min(lo[k], (double)b[k][0]);
+                if (std::isfinite(b[k][1])) hi[k] = std::max(hi[k], (double)b[k][1]);
+            }
+        }
+    double scale[3];
+    for (int k = 0; k < 3; k++) {
+        if (!(lo[k] <= hi[k])) lo[k] = hi[k] = 0.0;
+        const double ext = hi[k] - lo[k];
+        // cells 1 .. 32766 span the scene, cell 0 and 32767 are the outward margin
+        float sc = ext > 0 ? (float)(32765.0 / ext) : 1.0f;
+        if (!std::isfinite(sc) || sc <= 0.f) sc = 1.0f;
+        g.scale[k] = sc;
+        g.lo[k] = (float)(lo[k] - 1.0 / (double)sc);
+        // the float grid origin may sit a hair above the exact one: planes are computed from the float values below, so
+        // the outward rounding stays valid for what the kernel evaluates
+        scale[k] = (double)sc;
+    }
+    auto plane = [&](float x, int k, bool upper) -> uint32_t {
+        if (!std::isfinite(x)) return upper ? 32767u : 0u;
+        const double c = ((double)x - (double)g.lo[k]) * scale[k];
+        double q = upper ? std::ceil(c) + 1.0 : std::floor(c) - 1.0;
+        if (q < 0.0) q = 0.0;
+        if (q > 32767.0) q = 32767.0;
+        return (uint32_t)q;
+    };
+    out.resize(nodes.size());
+    for (size_t i = 0; i < nodes.size(); i++) {
+        const FlatNode &n = nodes[i];
+        QuantNode &q = out[i];
+        auto pack = [&](const float *b, int side, int k) -> uint32_t {
+            if (!(b[side * 2] <= b[side * 2 + 1])) return 0x0000u | (32767u);  // absent child: min 32767, max 0 (the duplicate leaf it points to is harmless)
+            return plane(b[side * 2], k, false) | (plane(b[side * 2 + 1], k, true) << 16);
+        };
+        q.lx = pack(n.bx, 0, 0); q.rx = pack(n.bx, 1, 0);
+        q.ly = pack(n.by, 0, 1); q.ry = pack(n.by, 1, 1);
+        q.lz = pack(n.bz, 0, 2); q.rz = pack(n.bz, 1, 2);
+        q.left = n.left;
+        q.right = n.right;
+    }
+    return g;
+}
+
+const char *validate_quantised(const std::vector<FlatNode> &nodes, const std::vector<QuantNode> &q, const QuantGrid &g, double *inflation) {
+    if (q.size() != nodes.size()) return "quantised node count differs";
+    double areaQ = 0, areaF = 0;
+    for (size_t i = 0; i < nodes.size(); i++) {
+        const FlatNode &n = nodes[i];
+        if (q[i].left != n.left || q[i].right != n.right) return "quantised node references differ";
+        const float *fb[3] = {n.bx, n.by, n.bz};
+        const uint32_t qb[3][2] = {{q[i].lx, q[i].rx}, {q[i].ly, q[i].ry}, {q[i].lz, q[i].rz}};
+        for (int side = 0; side < 2; side++) {
+            if (!(n.bx[side * 2] <= n.bx[side * 2 + 1])) continue;  // absent child
+            double eq[3], ef[3];
+            for (int k = 0; k < 3; k++) {
+                const float lo = fb[k][side * 2], hi = fb[k][side * 2 + 1];
+                const uint32_t w = qb[k][side];
+                const float qlo = (float)(w & 0xffffu), qhi = (float)(w >> 16);
+                if ((w & 0x8000u) || (w >> 31)) return "quantised plane exceeds 15 bits";
+                // the kernel's float evaluation of a point on the float box's planes
+                const float glo = (lo - g.lo[k]) * g.scale[k], ghi = (hi - g.lo[k]) * g.scale[k];
+                if (std::isfinite(lo) && !(qlo + 0.5f <= glo)) return "quantised lower plane is not below the box";
+                if (std::isfinite(hi) && !(qhi - 0.5f >= ghi)) return "quantised upper plane is not above the box";
+                eq[k] = (double)qhi - (double)qlo;
+                ef[k] = std::isfinite(lo) && std::isfinite(hi) ? ((double)hi - (double)lo) * (double)g.scale[k] : eq[k];
+            }
+            const int32_t ref = side ? n.right : n.left;
+            if (ref < 0) {  // mean over the leaves of (quantised area / float area)
+                const double aq = eq[0] * eq[1] + eq[1] * eq[2] + eq[2] * eq[0], af = ef[0] * ef[1] + ef[1] * ef[2] + ef[2] * ef[0];
+                if (af > 0) {
+                    areaQ += aq / af;
+                    areaF += 1.0;
+                }
+            }
+        }
+    }
+    if (inflation) *inflation = areaF > 0 ? areaQ / areaF : 1.0;
+    return "";
+}
+
 const char *validate_bvh(const BvhBuildResult &bvh, const std::vector<PrimBounds> &bounds) {
     const size_t n = bounds.size();
     if (bvh.nodes.empty()) return "no nodes";

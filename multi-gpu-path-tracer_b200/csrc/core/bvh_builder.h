@@ -31,6 +31,23 @@ struct alignas(64) FlatNode {
 };
 static_assert(sizeof(FlatNode) == 64, "FlatNode must be one 64-byte line");
 
+// The same two-child node in 32 bytes (two 16-byte quads, one sector): box planes as 15-bit integers on a uniform grid over
+// the scene's bounds, two planes per word (low half = min, high half = max):
+//   q[0] = (l.x, r.x, l.y, r.y)   q[1] = (l.z, r.z, left ref, right ref)
+// Planes are rounded outwards and moved one more cell outwards, so a quantised box always contains the float box; the
+// kernel tests rays in grid coordinates (trav_begin_grid).  Node i of this array is node i of `nodes`.
+struct alignas(32) QuantNode {
+    uint32_t lx, rx, ly, ry;
+    uint32_t lz, rz;
+    int32_t left, right;
+};
+static_assert(sizeof(QuantNode) == 32, "QuantNode must be 32 bytes");
+
+struct QuantGrid {
+    float lo[3];
+    float scale[3];  // g = (x - lo) * scale
+};
+
 // Wide node: up to four children, boxes as SoA so that one lane tests all four with independent instruction streams.
 // 128 bytes = eight 16-byte quads; the kernel fetches the first seven.
 //   q[0] = lo.x of children 0..3, q[1] = hi.x, q[2] = lo.y, q[3] = hi.y, q[4] = lo.z, q[5] = hi.z, q[6] = child refs (int32)
@@ -71,6 +88,14 @@ struct BvhBuildResult {
 
 // `bounds` must already include whatever conservative padding the caller wants.
 BvhBuildResult build_bvh(const std::vector<PrimBounds> &bounds, const BvhBuildOptions &opt);
+
+// Quantises the flat nodes; returns the grid.
+QuantGrid quantise_nodes(const std::vector<FlatNode> &nodes, std::vector<QuantNode> &out);
+
+// Checks, with the float arithmetic the kernel uses for ray origins, that every quantised box contains its float box with
+// at least half a cell to spare; `inflation` (may be null) receives the mean over the leaves of (surface area of the
+// quantised box / surface area of the float box), the price of the coarser planes.  Returns "" if valid.
+const char *validate_quantised(const std::vector<FlatNode> &nodes, const std::vector<QuantNode> &q, const QuantGrid &g, double *inflation);
 
 // Structural validation used by the tests: every primitive in exactly one leaf, child boxes
 // enclose their primitives, refs in range, depth within the device stack. Returns "" if valid.

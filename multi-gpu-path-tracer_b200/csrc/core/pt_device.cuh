@@ -31,6 +31,7 @@ struct TexDesc {
 
 struct DevScene {
     const float4 *nodes;   // 4 per node     (FlatNode, bvh_builder.h)
+    const uint4 *nodesq;   // 2 per node (QuantNode, bvh_builder.h): the same tree with 15-bit box planes on a scene-wide grid, 32 B per node
     const float4 *nodes4;  // 8 per wide node (FlatNode4): lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] refs[4] pad
     const float4 *prims;   // 3 per primitive in leaf order:
                            //   triangle: (v0.xyz, e1.x) (e1.yz, e2.xy) (e2.z, -, kind=0, -)
@@ -49,6 +50,8 @@ struct DevScene {
     double light_pick_scale;  // (n_lights - 1) + 0.999999, hitable_list.h:24
     float light_weight;       // 1.0f / n_lights, hitable_list.h:17
     int32_t pad;
+    float3 grid_lo, grid_scale;  // world -> grid of the quantised nodes: g = (x - grid_lo) * grid_scale, 0 <= g <= 32767
+    float pad2[2];
 };
 
 struct CamParams {  // camera.h:21-36, evaluated once per set_camera by a 1-thread device kernel
@@ -181,8 +184,12 @@ struct Hit {
 // triangle.h:63-113 with e1/e2 precomputed (the same float subtractions the reference redoes per test).
 // Branch-free: every lane evaluates the whole test and folds the reference's early-outs into one predicate;
 // the NaN behaviour of the original comparisons (u<0||u>1 etc. are false for NaN) is preserved.
+// `wins_ties`: whether this triangle replaces a current hit at EXACTLY the same t.  The reference keeps whichever of the two
+// its own tree reaches first (strict t < closest, bvh.h:202-205) — an order no other tree can reproduce; it happens where a
+// ray meets the shared edge of two triangles (measured: 3 pixels of a 1080p / 128-spp cornell_duck frame).  Here the lower
+// leaf-order position wins, which makes the image independent of the walk (kernel, node format, step schedule).
 __device__ __forceinline__ bool triangle_test(float3 v0, float3 e1, float3 e2, float3 o, float3 d, float tmin, float tmax,
-                                              float &t_out, float &u_out, float &v_out) {
+                                              float &t_out, float &u_out, float &v_out, bool wins_ties = false) {
     float3 pvec = cross(d, e2);
     float det = dot(e1, pvec);
     float inv_det = rcp_like_double(det);
@@ -192,7 +199,7 @@ __device__ __forceinline__ bool triangle_test(float3 v0, float3 e1, float3 e2, f
     float v = dot(d, qvec) * inv_det;
     float t = dot(e2, qvec) * inv_det;
     bool reject = (det < PT_DET_EPS_UP && det > -PT_DET_EPS_UP) | (u < 0) | (u > 1) | (v < 0) | (u + v > 1);
-    bool ok = !reject & (t < tmax) & (t > tmin);
+    bool ok = !reject & ((t < tmax) | ((t == tmax) & wins_ties)) & (t > tmin);
     t_out = t;
     u_out = u;
     v_out = v;
@@ -302,7 +309,7 @@ __device__ __forceinline__ Hit closest_hit(const DevScene &sc, float3 o, float3 
                     }
                 } else {
                     float t, u, w;
-                    if (triangle_test(f3(q0.x, q0.y, q0.z), f3(q0.w, q1.x, q1.y), f3(q1.z, q1.w, q2.x), o, d, tmin, best.t, t, u, w)) {
+                    if (triangle_test(f3(q0.x, q0.y, q0.z), f3(q0.w, q1.x, q1.y), f3(q1.z, q1.w, q2.x), o, d, tmin, best.t, t, u, w, k < best.prim)) {
                         best.t = t;
                         best.u = u;
                         best.v = w;
@@ -357,6 +364,15 @@ __device__ __forceinline__ void trav_begin(Trav &t, int32_t *stack, float3 o, fl
     t.best.u = t.best.v = 0.f;
     t.best.prim = -1;
 }
+// The same for the quantised nodes: the slab test runs in grid coordinates (g = (x - grid_lo) * grid_scale per axis, an affine
+// map that leaves the ray parameter t unchanged).  A stored plane p (15 bits) is turned into the float 2^15 + p by ONE byte
+// permute (exponent byte 0x47, p in mantissa bits 8..22), so the offset 2^15 is folded into the constant term here.
+__device__ __forceinline__ void trav_begin_grid(Trav &t, int32_t *stack, const DevScene &sc, float3 o, float3 d) {
+    trav_begin(t, stack, o, d);
+    const float3 og = f3((o.x - sc.grid_lo.x) * sc.grid_scale.x, (o.y - sc.grid_lo.y) * sc.grid_scale.y, (o.z - sc.grid_lo.z) * sc.grid_scale.z);
+    t.inv = slab_inverse(f3(d.x * sc.grid_scale.x, d.y * sc.grid_scale.y, d.z * sc.grid_scale.z));
+    t.oinv = f3(-(32768.0f + og.x) * t.inv.x, -(32768.0f + og.y) * t.inv.y, -(32768.0f + og.z) * t.inv.z);
+}
 __device__ __forceinline__ bool trav_finished(const Trav &t) { return t.cur == kTravDone && t.leaf_left == 0; }
 __device__ __forceinline__ void trav_hold_leaf(Trav &t, int32_t ref) {
     const int32_t v = ~ref;
@@ -365,14 +381,29 @@ __device__ __forceinline__ void trav_hold_leaf(Trav &t, int32_t ref) {
 }
 
 // one inner-node step (precondition: t.cur >= 0)
-template <bool COUNT>
+template <bool COUNT, bool QUANT = false>
 __device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, int32_t *stack, float tmin, uint32_t &n_box) {
     const float kSlack = 1.0000004f;
     const int32_t node = t.cur;
-    const float4 bx = __ldg(&sc.nodes[node * 4 + 0]);
-    const float4 by = __ldg(&sc.nodes[node * 4 + 1]);
-    const float4 bz = __ldg(&sc.nodes[node * 4 + 2]);
-    const int4 refs = __ldg(reinterpret_cast<const int4 *>(&sc.nodes[node * 4 + 3]));
+    float4 bx, by, bz;
+    int4 refs;
+    if (QUANT) {
+        const uint4 a = __ldg(&sc.nodesq[node * 2 + 0]);
+        const uint4 b = __ldg(&sc.nodesq[node * 2 + 1]);
+#define PT_PLANE_LO(w) __uint_as_float(__byte_perm((w), 0x47000000u, 0x7104))
+#define PT_PLANE_HI(w) __uint_as_float(__byte_perm((w), 0x47000000u, 0x7324))
+        bx = make_float4(PT_PLANE_LO(a.x), PT_PLANE_HI(a.x), PT_PLANE_LO(a.y), PT_PLANE_HI(a.y));
+        by = make_float4(PT_PLANE_LO(a.z), PT_PLANE_HI(a.z), PT_PLANE_LO(a.w), PT_PLANE_HI(a.w));
+        bz = make_float4(PT_PLANE_LO(b.x), PT_PLANE_HI(b.x), PT_PLANE_LO(b.y), PT_PLANE_HI(b.y));
+#undef PT_PLANE_LO
+#undef PT_PLANE_HI
+        refs = make_int4((int32_t)b.z, (int32_t)b.w, 0, 0);
+    } else {
+        bx = __ldg(&sc.nodes[node * 4 + 0]);
+        by = __ldg(&sc.nodes[node * 4 + 1]);
+        bz = __ldg(&sc.nodes[node * 4 + 2]);
+        refs = __ldg(reinterpret_cast<const int4 *>(&sc.nodes[node * 4 + 3]));
+    }
     if (COUNT) n_box += 2;
     float lx0 = fmaf(bx.x, t.inv.x, t.oinv.x), lx1 = fmaf(bx.y, t.inv.x, t.oinv.x);
     float ly0 = fmaf(by.x, t.inv.y, t.oinv.y), ly1 = fmaf(by.y, t.inv.y, t.oinv.y);
@@ -472,7 +503,7 @@ __device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, int3
         }
     } else {
         float tt, u, w;
-        if (triangle_test(f3(q0.x, q0.y, q0.z), f3(q0.w, q1.x, q1.y), f3(q1.z, q1.w, q2.x), o, d, tmin, t.best.t, tt, u, w)) {
+        if (triangle_test(f3(q0.x, q0.y, q0.z), f3(q0.w, q1.x, q1.y), f3(q1.z, q1.w, q2.x), o, d, tmin, t.best.t, tt, u, w, k < t.best.prim)) {
             t.best.t = tt;
             t.best.u = u;
             t.best.v = w;

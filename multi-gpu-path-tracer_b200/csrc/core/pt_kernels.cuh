@@ -176,8 +176,9 @@ __global__ void __launch_bounds__(kBlockThreads) pt_persistent_kernel(const __gr
 // waiting the warp leaves TRAVERSE, shades exactly those lanes (they get their bounce ray or the next camera
 // ray) and re-enters with the unfinished lanes resuming where they stopped — warp-level ray compaction without
 // moving any state between lanes, which the one-XORWOW-stream-per-pixel contract forbids.
-template <bool SPHERES, bool RTOW, bool COUNT, bool WIDE>
+template <bool SPHERES, bool RTOW, bool COUNT, int NODES>  // NODES: 0 = 64-byte two-child nodes, 1 = four-wide nodes, 2 = 32-byte quantised two-child nodes
 __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __grid_constant__ RenderParams p) {
+    constexpr bool WIDE = NODES == 1, QUANT = NODES == 2;
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t total_items = work_total(p);
     const int refill_at = p.refill_at;
@@ -193,7 +194,8 @@ __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __
     unsigned long long acc_box = 0, acc_tri = 0, acc_light = 0;
     int32_t stack[kStackSize];
     Trav tr;
-    trav_begin(tr, stack, ro, rd);
+    if (QUANT) trav_begin_grid(tr, stack, p.scene, ro, rd);
+    else trav_begin(tr, stack, ro, rd);
     trav_idle(tr);
 
     for (;;) {
@@ -235,7 +237,8 @@ __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __
                 samples_done++;  // camera.h:52,82: the loop body never runs
             } else {
                 have_path = true;
-                trav_begin(tr, stack, ro, rd);
+                if (QUANT) trav_begin_grid(tr, stack, p.scene, ro, rd);
+                else trav_begin(tr, stack, ro, rd);
                 n_rays++;
                 pixel_rays++;
             }
@@ -256,13 +259,13 @@ __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __
             if (n_active == 0 || n_paths - n_active >= wait_for) break;
             if (__popc(m_node) >= __popc(m_prim)) {
                 if (!WIDE && node_burst == 2) {  // the default, without the loop bookkeeping
-                    if (can_node) trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
-                    if (tr.cur >= 0) trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
+                    if (can_node) trav_node_step<COUNT, QUANT>(p.scene, tr, stack, 0.001f, n_box);
+                    if (tr.cur >= 0) trav_node_step<COUNT, QUANT>(p.scene, tr, stack, 0.001f, n_box);
                 } else {
                     for (int k = 0; k < node_burst; k++)
                         if (tr.cur >= 0) {
                             if (WIDE) trav_node_step4<COUNT>(p.scene, tr, stack, 0.001f, n_box);
-                            else trav_node_step<COUNT>(p.scene, tr, stack, 0.001f, n_box);
+                            else trav_node_step<COUNT, QUANT>(p.scene, tr, stack, 0.001f, n_box);
                         }
                 }
             } else {
@@ -276,7 +279,8 @@ __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __
             bool cont = shade<SPHERES, RTOW, COUNT>(p.scene, tr.best, ro, rd, att, rng, contrib, n_light);
             bounce++;
             if (cont && bounce < p.depth) {
-                trav_begin(tr, stack, ro, rd);
+                if (QUANT) trav_begin_grid(tr, stack, p.scene, ro, rd);
+                else trav_begin(tr, stack, ro, rd);
                 n_rays++;
                 pixel_rays++;
             } else {
@@ -384,7 +388,9 @@ __global__ void __launch_bounds__(kBlockThreads) pt_direct_kernel(const __grid_c
 // Debug/parity probe: one thread walks ONE pixel exactly like the render kernels do and records every ray
 // (16 floats per event: sample, bounce, original primitive id or -1, t, bary u, bary v, origin xyz, direction xyz,
 // throughput xyz before shading, 0).  Used by tests to find the first event where CUDA and the oracle part ways.
-template <bool SPHERES, bool RTOW>
+// MODE 0 walks the tree with closest_hit (per-lane loop); MODE 1 / 2 with the resumable steps of the wavefront kernel on the
+// 64-byte / the quantised nodes.
+template <bool SPHERES, bool RTOW, int MODE>
 __global__ void pt_trace_kernel(const __grid_constant__ RenderParams p, int px, int py, float *events, int max_events, int *n_events, float *col_out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int pixel_index = ((int)p.height - py - 1) * (int)p.width + px;
@@ -401,7 +407,20 @@ __global__ void pt_trace_kernel(const __grid_constant__ RenderParams p, int px, 
         float3 att = f3(1.0f, 1.0f, 1.0f);
         float3 contrib = f3(0.0f, 0.0f, 0.0f);
         for (uint32_t i = 0; i < p.depth; i++) {
-            Hit h = closest_hit<SPHERES, false>(p.scene, ro, rd, 0.001f, nb, nt);
+            Hit h;
+            if (MODE == 0) {
+                h = closest_hit<SPHERES, false>(p.scene, ro, rd, 0.001f, nb, nt);
+            } else {
+                int32_t stack[kStackSize];
+                Trav tr;
+                if (MODE == 2) trav_begin_grid(tr, stack, p.scene, ro, rd);
+                else trav_begin(tr, stack, ro, rd);
+                while (!trav_finished(tr)) {
+                    if (tr.cur >= 0) trav_node_step<false, MODE == 2>(p.scene, tr, stack, 0.001f, nb);
+                    else trav_prim_step<SPHERES, false>(p.scene, tr, stack, ro, rd, 0.001f, nt);
+                }
+                h = tr.best;
+            }
             if (n < max_events) {
                 float *e = events + (size_t)n * 16;
                 e[0] = (float)s; e[1] = (float)i;

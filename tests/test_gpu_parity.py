@@ -143,6 +143,12 @@ def test_direct_kernel_equals_persistent_kernel(tracer, duck, ptb):
     assert np.array_equal(a, b) and np.array_equal(ya, yb)
     c, yc = render(tracer, duck, 120, 68, 6, 6, kernel=ptb.PT_KERNEL_LOCKSTEP, ptb=ptb)
     assert np.array_equal(a, c) and np.array_equal(ya, yc)
+    # 64-byte float nodes / 32-byte quantised nodes (looser boxes): same closest hits
+    for fmt in (ptb.PT_NODES_FULL, ptb.PT_NODES_QUANTISED):
+        tracer.set_option(ptb.PT_OPT_NODE_FORMAT, fmt)
+        q, yq = render(tracer, duck, 120, 68, 6, 6, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
+        assert np.array_equal(a, q) and np.array_equal(ya, yq)
+    tracer.set_option(ptb.PT_OPT_NODE_FORMAT, ptb.PT_NODES_AUTO)
     # the step-scheduling knobs only change WHEN lanes run which step, never pixels
     for refill_at, burst, width in ((1, 1, 2), (5, 3, 4), (32, 2, 2), (20, 4, 4)):
         tracer.set_option(ptb.PT_OPT_REFILL_AT, refill_at)
@@ -317,3 +323,18 @@ def test_full_size_properties_1080p(tracer, duck, oracle):
         check(full[rows], ref[rows], spp)
     # about a fifth of the pixels leave through the open front of the box and stay black
     assert 0.10 < float((full.max(axis=2) == 0).mean()) < 0.35
+
+
+def test_image_does_not_depend_on_the_walk_at_full_size(tracer, duck, ptb):
+    """1080p / 96 spp: enough samples for rays that meet the shared edge of two triangles at exactly the same t (about 1e-8 per
+    sample).  The tie rule (lower leaf-order position wins) makes kernels and node formats agree on those too."""
+    w, h, spp, depth = 1920, 1080, 96, 10
+    tracer.set_option(ptb.PT_OPT_NODE_FORMAT, ptb.PT_NODES_FULL)
+    a, ya = render(tracer, duck, w, h, spp, depth, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
+    tracer.set_option(ptb.PT_OPT_NODE_FORMAT, ptb.PT_NODES_QUANTISED)
+    b, yb = render(tracer, duck, w, h, spp, depth, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
+    tracer.set_option(ptb.PT_OPT_NODE_FORMAT, ptb.PT_NODES_AUTO)
+    c, yc = render(tracer, duck, w, h, spp, depth, kernel=ptb.PT_KERNEL_DIRECT, ptb=ptb)
+    tracer.set_option(ptb.PT_OPT_KERNEL, ptb.PT_KERNEL_PERSISTENT)
+    assert np.array_equal(a, b) and np.array_equal(ya, yb)
+    assert np.array_equal(a, c) and np.array_equal(ya, yc)
