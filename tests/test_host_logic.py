@@ -197,6 +197,12 @@ def test_bvh_is_structurally_valid_for_fixtures_and_edge_cases(ptb, core_lib, du
         assert st["bvh_depth"] <= 48 and st["bvh_leaves"] >= len(scene.tri_mat) / leaf
     ok, msg, st = ptb.bvh_selftest(duck, 4)
     assert 1500 < st["bvh_nodes"] < 4224 and st["bvh_depth"] < 30
+    # quantised nodes (the self-test also checks that every 15-bit box contains its float box with half a cell to spare):
+    # close to the float boxes for the duck, far too coarse for the sphere field inside its 5000-unit sky sphere
+    assert 1.0 <= st["quant_inflation"] < 1.05
+    field, _ = ptb.scenes.rtow_sphere_field()
+    ok, msg, st = ptb.bvh_selftest(field, 4)
+    assert ok and st["quant_inflation"] > 3.0, (msg, st["quant_inflation"])
     rng = np.random.default_rng(1)
     mats = np.zeros(1, ptb.MAT_DTYPE)
     mats["type"] = ptb.PT_MAT_UNIVERSAL
