@@ -6,6 +6,7 @@ Outputs (git-ignored, shipped to the GPU box by gpurun):
     multi-gpu-path-tracer_b200/_lib/libptcore.so     the C ABI of include/ptcore.h (CUDA kernels, sm_100a)
     multi-gpu-path-tracer_b200/_lib/ptscene_tool     scene converter
     multi-gpu-path-tracer_b200/_lib/cuda_project     host executable mirroring the reference's CLI
+    multi-gpu-path-tracer_b200/_lib/host_api_test, gpu_monitor_test   C++ tests of the host mirror
 """
 from __future__ import annotations
 
@@ -84,14 +85,19 @@ def build_tools(force: bool = False, verbose: bool = False) -> None:
         deps = list((CSRC / "host").glob("*.h")) + [test_src, CSRC / "host" / "SceneLoader.cpp", ROOT / "include" / "ptcore.h"]
         if force or _stale(exe, deps) or _stale(exe, [LIBDIR / "libptcore.so"]):
             _run([HOST_CXX, "-std=c++17", "-O2", "-pthread", f"-I{CUDA_HOME}/include", f"-I{ROOT / 'include'}", test_src,
-                  f"-L{LIBDIR}", "-lptcore", f"-L{CUDA_HOME}/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{CUDA_HOME}/lib64", "-o", exe], verbose)
+                  f"-L{LIBDIR}", "-lptcore", f"-L{CUDA_HOME}/lib64", "-lcudart", "-ldl", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{CUDA_HOME}/lib64", "-o", exe], verbose)
+    mon_src = CSRC / "host" / "gpu_monitor_test.cpp"
+    if mon_src.exists():
+        exe = LIBDIR / "gpu_monitor_test"
+        if force or _stale(exe, [mon_src, CSRC / "host" / "GPUMonitor.h", CSRC / "host" / "Renderer.h"]):
+            _run([HOST_CXX, "-std=c++17", "-O2", "-pthread", mon_src, "-ldl", "-o", exe], verbose)
     cli_src = CSRC / "host" / "main.cpp"
     if cli_src.exists():
         cli = LIBDIR / "cuda_project"
         deps = list((CSRC / "host").glob("*.h")) + [cli_src, ROOT / "include" / "ptcore.h"]
         if force or _stale(cli, deps) or _stale(cli, [LIBDIR / "libptcore.so"]):
             _run([HOST_CXX, "-std=c++17", "-O2", "-pthread", f"-I{CUDA_HOME}/include", f"-I{ROOT / 'include'}", cli_src,
-                  f"-L{LIBDIR}", "-lptcore", f"-L{CUDA_HOME}/lib64", "-lcudart", f"-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{CUDA_HOME}/lib64", "-o", cli], verbose)
+                  f"-L{LIBDIR}", "-lptcore", f"-L{CUDA_HOME}/lib64", "-lcudart", "-ldl", f"-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{CUDA_HOME}/lib64", "-o", cli], verbose)
 
 
 def build_all(force: bool = False, verbose: bool = False) -> Path:

@@ -3,6 +3,7 @@
 // parameters the reference can only receive over its websocket:
 //   --width N --height N --spp N --depth N --gpus N --streams N --block BXxBY --scheduler fsfl|dsfl|dsdl|dynamic
 //   --tile WxH --out file.ppm --frames N --vfov F --hfov F --lookfrom x,y,z --front x,y,z --show-tasks 0|1
+//   --monitor 0|1 (the reference's monitor thread: NVML figures + RENDER_STATS# messages every 500 ms)
 #pragma once
 
 #include "RendererConfig.h"
@@ -43,6 +44,7 @@ public:
             else if (a == "--vfov") config.vfov = std::stof(next());
             else if (a == "--hfov") config.hfov = std::stof(next());
             else if (a == "--show-tasks") config.showTasks = std::stoi(next()) != 0;
+            else if (a == "--monitor") monitor = std::stoi(next()) != 0;
             else if (a == "--max-tasks-in-row") config.maxTasksInRow = (unsigned)std::stoul(next());
             else if (a == "--block") { unsigned x = 8, y = 8; parse2(next(), 'x', x, y); config.threadBlockSize = dim3(x, y); }
             else if (a == "--tile") parse2(next(), 'x', config.dynamicTileWidth, config.dynamicTileHeight);
@@ -58,7 +60,7 @@ public:
             } else throw std::runtime_error("unknown argument " + a);
         }
     }
-    bool lookFromSet = false, frontSet = false;
+    bool lookFromSet = false, frontSet = false, monitor = false;
 
 private:
     static void parse2(const std::string &s, char sep, unsigned &a, unsigned &b) {

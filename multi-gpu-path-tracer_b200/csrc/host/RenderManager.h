@@ -17,6 +17,7 @@
 #include "CameraConfig.h"
 #include "DevicePathTracer.h"
 #include "Framebuffer.h"
+#include "GPUMonitor.h"
 #include "HostScene.h"
 #include "RendererConfig.h"
 #include "TaskGenerator.h"
@@ -206,6 +207,16 @@ public:
     }
 
     const FrameStats &lastFrameStats() const { return stats_; }
+
+    // reference :433-447: feed the monitor with the last frame's render time per GPU (the slowest of its workers) and the
+    // load imbalance (max / mean over the workers)
+    void updateMetrics(MonitorThread &monitorThreadObj) {
+        std::vector<double> perGpu(config_.gpuNumber, 0.0);
+        for (auto &w : workers_)
+            if (w.device >= 0 && (size_t)w.device < perGpu.size()) perGpu[(size_t)w.device] = std::max(perGpu[(size_t)w.device], w.ms);
+        for (size_t g = 0; g < perGpu.size(); g++) monitorThreadObj.updateTimeOfRendering((int)g, (float)perGpu[g]);
+        monitorThreadObj.updateImbalance((float)stats_.imbalance);
+    }
     const std::vector<RenderTask> &tasks() const { return renderTasks_; }
     std::vector<std::shared_ptr<DevicePathTracer>> &tracers() { return devicePathTracers_; }
 

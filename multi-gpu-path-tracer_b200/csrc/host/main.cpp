@@ -5,6 +5,7 @@
 #include "ArgumentLoader.h"
 #include "CameraConfig.h"
 #include "FileRenderer.h"
+#include "GPUMonitor.h"
 #include "HostScene.h"
 #include "RenderManager.h"
 #include "RendererConfig.h"
@@ -12,6 +13,8 @@
 #include <chrono>
 #include <cstdio>
 #include <iostream>
+#include <memory>
+#include <thread>
 
 int main(int argc, char **argv) {
     RendererConfig config;
@@ -45,6 +48,14 @@ int main(int argc, char **argv) {
     FileRenderer fileRenderer(config, manager.getFramebuffer());
     Renderer &renderer = fileRenderer;
 
+    // reference src/main.cu:76-77: the monitor runs beside the render loop (here only on request: the headless run is short)
+    std::unique_ptr<MonitorThread> monitorObj;
+    std::thread monitorThread;
+    if (argLoader.monitor) {
+        monitorObj.reset(new MonitorThread(renderer));
+        monitorThread = std::thread(std::ref(*monitorObj));
+    }
+
     double last_ms = 0;
     while (!renderer.shouldStopRendering()) {
         auto start = std::chrono::high_resolution_clock::now();
@@ -53,6 +64,14 @@ int main(int argc, char **argv) {
         last_ms = std::chrono::duration<double, std::milli>(stop - start).count();
         std::cout << "Path Tracing took: " << (long long)last_ms << "ms" << std::endl;
         renderer.renderFrame();
+        if (monitorObj) {  // reference src/main.cu:87-88
+            manager.updateMetrics(*monitorObj);
+            monitorObj->updateFps();
+        }
+    }
+    if (monitorObj) {
+        monitorObj->safeTerminate();
+        monitorThread.join();
     }
     uint64_t rays = 0, samples = 0;
     for (auto &t : manager.tracers()) {

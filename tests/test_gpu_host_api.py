@@ -74,3 +74,24 @@ def test_render_manager_runtime_api(duck_file):
     r = subprocess.run([str(exe), str(duck_file)], capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:])
     assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
+
+
+def test_monitor_thread_reports_nvml_figures_and_render_times(tmp_path, duck_file):
+    """The reference's monitor (src/Profiling/GPUMonitor.cpp, src/main.cu:76-93): NVML figures per GPU, time of rendering and
+    imbalance from RenderManager::updateMetrics, sent as RENDER_STATS# messages while frames are rendered."""
+    mon = ROOT / "multi-gpu-path-tracer_b200" / "_lib" / "gpu_monitor_test"
+    if not CLI.exists() or not mon.exists():
+        pytest.skip("host binaries not built")
+    r = subprocess.run([str(mon)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "GPU_MONITOR_TEST_OK" in r.stdout and "nvml available: 1" in r.stdout, r.stdout[-800:]
+    out = tmp_path / "m.ppm"
+    r = subprocess.run([str(CLI), "7", str(duck_file), "--out", str(out), "--width", 640, "--height", 360, "--spp", 256, "--depth", 10, "--frames", 12, "--monitor", 1],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    msgs = [ln for ln in r.stdout.splitlines() if ln.startswith("RENDER_STATS#")]
+    assert msgs, r.stdout[-800:]
+    fields = msgs[-1][len("RENDER_STATS#"):].split("|")
+    triples = {fields[i + 1]: (fields[i], fields[i + 2]) for i in range(0, len(fields) - 2, 3)}
+    assert triples["Mem Total GPU 0"][0] == "MB" and float(triples["Mem Total GPU 0"][1]) > 100000  # 180 GB of HBM3e
+    assert "GPU Util GPU 0" in triples and "TOR 0" in triples and "Imbalance 0" in triples
+    assert any(float(dict((f[i + 1], f[i + 2]) for i in range(0, len(f) - 2, 3))["TOR 0"]) > 0 for f in (m[len("RENDER_STATS#"):].split("|") for m in msgs))

@@ -248,3 +248,13 @@ def test_exhaustive_exactness_of_reciprocal_and_div_by_pi(tmp_path):
     subprocess.run(["/usr/bin/gcc", "-O2", "-ffp-contract=off", "-fopenmp", str(ROOT / "tests" / "c" / "exactness_check.c"), "-lm", "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, timeout=600).stdout
     assert "double mismatches 0, float-result mismatches 0" in out and "rcp:" in out and out.strip().endswith("mismatches 0"), out
+
+
+def test_gpu_monitor_accumulators_and_wire_format_without_a_gpu(core_lib):
+    """csrc/host/GPUMonitor.h (reference src/Profiling/GPUMonitor.{h,cpp}): NVML is opened at run time, so the test binary
+    runs here too (no devices: empty statistics) — accumulators, RENDER_STATS# prefix, monitor thread start/stop."""
+    import subprocess
+    exe = ROOT / "multi-gpu-path-tracer_b200" / "_lib" / "gpu_monitor_test"
+    assert exe.exists(), "run __graft_entry__.build()"
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "GPU_MONITOR_TEST_OK" in r.stdout, r.stdout
