@@ -114,6 +114,31 @@ def test_cuda_is_bit_exact_with_live_reference_cuda_renderer(tracer, duck):
     assert valid >= 1, "the reference rendered without lights at every candidate size"
 
 
+def test_live_reference_cuda_renderer_at_full_size(tracer, duck):
+    """Gate A at BASELINE config 2's geometry (1920x1080, depth 10) with 32 spp, against the reference's CUDA renderer run here.
+    Every pixel is expected to be identical except where a ray meets the shared edge of two triangles at exactly the same t
+    (the winner depends on the reference's own tree; about 1e-8 per sample, i.e. a handful of the 2 M pixels,
+    each off by one sample's worth)."""
+    ref_gpu = ROOT / "oracle" / "_ref" / "ref_gpu"
+    if not ref_gpu.exists():
+        pytest.skip("oracle/_ref/ref_gpu did not travel to this box")
+    w, h, spp, depth = 1920, 1080, 32, 10
+    with tempfile.TemporaryDirectory() as td:
+        flat, ppm = Path(td) / "duck.ptscene", Path(td) / "ref.ppm"
+        flat.write_bytes(duck.to_ptscene_bytes())
+        r = subprocess.run([str(ref_gpu), str(flat), str(w), str(h), str(spp), str(depth), str(ppm)], capture_output=True, text=True, timeout=900)
+        if r.returncode != 0 or "REF_GPU_JSON" not in r.stdout:
+            pytest.skip(f"ref_gpu could not run here: {(r.stderr or r.stdout)[-200:]}")
+        ref = np.array(Image.open(ppm).convert("RGB"))
+    rgb, _ = render(tracer, duck, w, h, spp, depth)
+    if ref.mean() < 0.5 * rgb.mean():
+        pytest.skip("the reference lost its lights at this size (use-after-free, see the test above)")
+    diff = np.abs(rgb.astype(np.int32) - ref.astype(np.int32)).max(axis=2)
+    n_diff, max_diff = int((diff > 0).sum()), int(diff.max())
+    print(dict(pixels=w * h, differing=n_diff, max_abs_diff=max_diff))
+    assert n_diff <= 24 and max_diff <= 2 * 256 // spp, (n_diff, max_diff, np.argwhere(diff > 0)[:8].tolist())
+
+
 @pytest.mark.parametrize("w,h,spp,depth,camera", [
     (160, 90, 8, 10, None),
     (96, 54, 64, 8, None),
