@@ -259,6 +259,7 @@ def main():
     if args.node_format:
         pt.set_option(ptb200.PT_OPT_NODE_FORMAT, args.node_format)
 
+
     tw, th = (int(x) for x in args.tile.split("x"))
     if world == 1:
         tiles = [(0, 0, WIDTH, HEIGHT)]

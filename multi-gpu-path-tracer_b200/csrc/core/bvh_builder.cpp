@@ -271,7 +271,7 @@ struct Builder {
     }
 };
 
-inline int32_t leaf_ref(int32_t first, int32_t count) { return ~((first << kLeafCountBits) | (count - 1)); }
+inline int32_t leaf_ref(int32_t first, int32_t count) { return ~((first << kLeafCountBits) | count); }
 
 }  // namespace
 
@@ -552,7 +552,7 @@ const char *validate_bvh(const BvhBuildResult &bvh, const std::vector<PrimBounds
                 W c{ref, w.depth + 1, {lo[0], lo[1], lo[2]}, {hi[0], hi[1], hi[2]}};
                 st.push_back(c);
             } else {
-                int32_t v = ~ref, first = v >> kLeafCountBits, count = (v & (kMaxLeafPrims - 1)) + 1;
+                int32_t first = leaf_first(ref), count = leaf_count(ref);
                 if (first < 0 || (size_t)first + (size_t)count > n) return "leaf range out of bounds";
                 for (int32_t i = 0; i < count; i++) {
                     if (seenPos[(size_t)first + (size_t)i]) return "leaf ranges overlap";
@@ -598,7 +598,7 @@ const char *validate_bvh4(const BvhBuildResult &bvh, const std::vector<PrimBound
                 W cw{ref, w.depth + 1, {lo[0], lo[1], lo[2]}, {hi[0], hi[1], hi[2]}};
                 st.push_back(cw);
             } else {
-                int32_t v = ~ref, first = v >> kLeafCountBits, count = (v & (kMaxLeafPrims - 1)) + 1;
+                int32_t first = leaf_first(ref), count = leaf_count(ref);
                 if (first < 0 || (size_t)first + (size_t)count > n) return "wide leaf range out of bounds";
                 for (int32_t i = 0; i < count; i++) {
                     if (seenPos[(size_t)first + (size_t)i]) return "wide leaf ranges overlap";

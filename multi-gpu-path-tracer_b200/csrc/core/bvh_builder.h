@@ -21,7 +21,7 @@ namespace ptc {
 //   q[1] = (l.min.y, l.max.y, r.min.y, r.max.y)
 //   q[2] = (l.min.z, l.max.z, r.min.z, r.max.z)
 //   q[3] = (left ref, right ref, unused, unused) as int32
-// child ref >= 0: index of an inner node; ref < 0: leaf, ~ref = (first_prim << 3) | (count - 1).
+// child ref >= 0: index of an inner node; ref < 0: leaf, ~ref = (first_prim << 4) | count, 1 <= count <= 8.
 // An absent child (single-leaf scenes) has an inverted box (+inf, -inf) that no ray enters.
 struct alignas(64) FlatNode {
     float bx[4];
@@ -60,8 +60,10 @@ struct alignas(128) FlatNode4 {
 };
 static_assert(sizeof(FlatNode4) == 128, "FlatNode4 must be 128 bytes");
 
-constexpr int kLeafCountBits = 3;
-constexpr int kMaxLeafPrims = 1 << kLeafCountBits;  // 8
+constexpr int kLeafCountBits = 4;   // ~ref = (first << 4) | count: the complement IS the kernel's leaf cursor (position << 4 | primitives left)
+constexpr int kMaxLeafPrims = 8;
+inline int32_t leaf_first(int32_t ref) { return (~ref) >> kLeafCountBits; }
+inline int32_t leaf_count(int32_t ref) { return (~ref) & ((1 << kLeafCountBits) - 1); }
 constexpr int kMaxTraversalDepth = 48;              // BVH2 depth bound; the device stack (64 entries) covers it for both node widths
 
 struct PrimBounds {

@@ -198,7 +198,7 @@ __device__ __forceinline__ bool triangle_test(float3 v0, float3 e1, float3 e2, f
     float3 qvec = cross(tvec, e1);
     float v = dot(d, qvec) * inv_det;
     float t = dot(e2, qvec) * inv_det;
-    bool reject = (det < PT_DET_EPS_UP && det > -PT_DET_EPS_UP) | (u < 0) | (u > 1) | (v < 0) | (u + v > 1);
+    bool reject = (fabsf(det) < PT_DET_EPS_UP) | (u < 0) | (u > 1) | (v < 0) | (u + v > 1);
     bool ok = !reject & ((t < tmax) | ((t == tmax) & wins_ties)) & (t > tmin);
     t_out = t;
     u_out = u;
@@ -291,9 +291,9 @@ __device__ __forceinline__ Hit closest_hit(const DevScene &sc, float3 o, float3 
             if (hl) { node = refs.x; continue; }
             if (hr) { node = refs.y; continue; }
         } else {
-            const int32_t v = ~node;
-            const int32_t first = v >> 3;
-            const int32_t count = (v & 7) + 1;
+            const int32_t v = ~node;  // (first << 4) | count, bvh_builder.h
+            const int32_t first = v >> 4;
+            const int32_t count = v & 15;
             for (int32_t i = 0; i < count; i++) {
                 const int32_t k = first + i;
                 const float4 q0 = __ldg(&sc.prims[k * 3 + 0]);
@@ -332,30 +332,31 @@ __device__ __forceinline__ Hit closest_hit(const DevScene &sc, float3 o, float3 
 // ----------------------------------------------------------------------------------------
 constexpr int32_t kTravDone = (int32_t)0x80000000;  // `cur` when nothing is left to visit: negative, but never a valid leaf reference
 
-// Lane state of a resumable traversal.  Encodings are chosen so that the two warp votes are single compares:
+// Lane state of a resumable traversal.  Encodings are chosen so that the two warp votes are single instructions:
 //   can take a node step       <=>  cur >= 0
-//   can take a primitive step  <=>  leaf_left > 0
+//   can take a primitive step  <=>  (leaf & 15) != 0
 // stack[0] always holds kTravDone, so a pop never needs an emptiness check.
 struct Trav {
     int32_t cur;        // >= 0 inner node, < 0 leaf reference (blocked until the held leaf is done), kTravDone = exhausted
-    int32_t leaf_next;  // next primitive of the held leaf (leaf-order position)
-    int32_t leaf_left;  // primitives of the held leaf still to test (0 = no leaf held)
+    int32_t leaf;       // cursor of the held leaf: (next primitive position << 4) | primitives left; the complement of a leaf
+                        // reference is such a cursor, and "+ 15" moves it on by one primitive
     int32_t sp;
     float3 inv, oinv;
+    uint3 sel, self;    // quantised nodes: byte-permute selectors of the plane the ray reaches first / last, per axis
     Hit best;
 };
 
+__device__ __forceinline__ bool trav_leaf_held(const Trav &t) { return (t.leaf & 15) != 0; }
 __device__ __forceinline__ void trav_push(Trav &t, int32_t *stack, int32_t x) { stack[t.sp++] = x; }
 __device__ __forceinline__ int32_t trav_pop(Trav &t, int32_t *stack) { return stack[--t.sp]; }
 
 __device__ __forceinline__ void trav_idle(Trav &t) {
     t.cur = kTravDone;
-    t.leaf_left = 0;
+    t.leaf = 0;
 }
 __device__ __forceinline__ void trav_begin(Trav &t, int32_t *stack, float3 o, float3 d) {
     t.cur = 0;
-    t.leaf_next = 0;
-    t.leaf_left = 0;
+    t.leaf = 0;
     stack[0] = kTravDone;
     t.sp = 1;
     t.inv = slab_inverse(d);
@@ -372,12 +373,18 @@ __device__ __forceinline__ void trav_begin_grid(Trav &t, int32_t *stack, const D
     const float3 og = f3((o.x - sc.grid_lo.x) * sc.grid_scale.x, (o.y - sc.grid_lo.y) * sc.grid_scale.y, (o.z - sc.grid_lo.z) * sc.grid_scale.z);
     t.inv = slab_inverse(f3(d.x * sc.grid_scale.x, d.y * sc.grid_scale.y, d.z * sc.grid_scale.z));
     t.oinv = f3(-(32768.0f + og.x) * t.inv.x, -(32768.0f + og.y) * t.inv.y, -(32768.0f + og.z) * t.inv.z);
+    // low half of a word = min plane (selector 0x7104), high half = max plane (0x7324); a ray going down an axis meets max first
+    t.sel = make_uint3(t.inv.x < 0.f ? 0x7324u : 0x7104u, t.inv.y < 0.f ? 0x7324u : 0x7104u, t.inv.z < 0.f ? 0x7324u : 0x7104u);
+    t.self = make_uint3(t.sel.x ^ 0x0220u, t.sel.y ^ 0x0220u, t.sel.z ^ 0x0220u);
 }
-__device__ __forceinline__ bool trav_finished(const Trav &t) { return t.cur == kTravDone && t.leaf_left == 0; }
-__device__ __forceinline__ void trav_hold_leaf(Trav &t, int32_t ref) {
-    const int32_t v = ~ref;
-    t.leaf_next = v >> 3;
-    t.leaf_left = (v & 7) + 1;
+__device__ __forceinline__ bool trav_finished(const Trav &t) { return t.cur == kTravDone && !trav_leaf_held(t); }
+__device__ __forceinline__ void trav_hold_leaf(Trav &t, int32_t ref) { t.leaf = ~ref; }
+
+// prmt.b32 without the selector masking that __byte_perm adds (the selectors here are plain byte indices)
+__device__ __forceinline__ float plane_float(uint32_t word, uint32_t selector) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(0x47000000u), "r"(selector));
+    return __uint_as_float(r);
 }
 
 // one inner-node step (precondition: t.cur >= 0)
@@ -385,36 +392,46 @@ template <bool COUNT, bool QUANT = false>
 __device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, int32_t *stack, float tmin, uint32_t &n_box) {
     const float kSlack = 1.0000004f;
     const int32_t node = t.cur;
-    float4 bx, by, bz;
+    float ln, lf, rn, rf;
     int4 refs;
     if (QUANT) {
         const uint4 a = __ldg(&sc.nodesq[node * 2 + 0]);
         const uint4 b = __ldg(&sc.nodesq[node * 2 + 1]);
-#define PT_PLANE_LO(w) __uint_as_float(__byte_perm((w), 0x47000000u, 0x7104))
-#define PT_PLANE_HI(w) __uint_as_float(__byte_perm((w), 0x47000000u, 0x7324))
-        bx = make_float4(PT_PLANE_LO(a.x), PT_PLANE_HI(a.x), PT_PLANE_LO(a.y), PT_PLANE_HI(a.y));
-        by = make_float4(PT_PLANE_LO(a.z), PT_PLANE_HI(a.z), PT_PLANE_LO(a.w), PT_PLANE_HI(a.w));
-        bz = make_float4(PT_PLANE_LO(b.x), PT_PLANE_HI(b.x), PT_PLANE_LO(b.y), PT_PLANE_HI(b.y));
-#undef PT_PLANE_LO
-#undef PT_PLANE_HI
+        if (COUNT) n_box += 2;
+        // plane p -> float 2^15 + p by one byte permute; the selector picks the half of the word that the ray reaches first /
+        // last on this axis (t.sel, from the sign of the direction), so no per-axis min / max is needed
+        const uint32_t nx = t.sel.x, ny = t.sel.y, nz = t.sel.z;
+        const uint32_t fx = t.self.x, fy = t.self.y, fz = t.self.z;
+#define PT_PLANE(w, s) plane_float((w), (s))
+        const float lnx = fmaf(PT_PLANE(a.x, nx), t.inv.x, t.oinv.x), lfx = fmaf(PT_PLANE(a.x, fx), t.inv.x, t.oinv.x);
+        const float rnx = fmaf(PT_PLANE(a.y, nx), t.inv.x, t.oinv.x), rfx = fmaf(PT_PLANE(a.y, fx), t.inv.x, t.oinv.x);
+        const float lny = fmaf(PT_PLANE(a.z, ny), t.inv.y, t.oinv.y), lfy = fmaf(PT_PLANE(a.z, fy), t.inv.y, t.oinv.y);
+        const float rny = fmaf(PT_PLANE(a.w, ny), t.inv.y, t.oinv.y), rfy = fmaf(PT_PLANE(a.w, fy), t.inv.y, t.oinv.y);
+        const float lnz = fmaf(PT_PLANE(b.x, nz), t.inv.z, t.oinv.z), lfz = fmaf(PT_PLANE(b.x, fz), t.inv.z, t.oinv.z);
+        const float rnz = fmaf(PT_PLANE(b.y, nz), t.inv.z, t.oinv.z), rfz = fmaf(PT_PLANE(b.y, fz), t.inv.z, t.oinv.z);
+#undef PT_PLANE
+        ln = fmaxf(fmaxf(lnx, lny), fmaxf(lnz, tmin));
+        lf = fminf(fminf(lfx, lfy), fminf(lfz, t.best.t));
+        rn = fmaxf(fmaxf(rnx, rny), fmaxf(rnz, tmin));
+        rf = fminf(fminf(rfx, rfy), fminf(rfz, t.best.t));
         refs = make_int4((int32_t)b.z, (int32_t)b.w, 0, 0);
     } else {
-        bx = __ldg(&sc.nodes[node * 4 + 0]);
-        by = __ldg(&sc.nodes[node * 4 + 1]);
-        bz = __ldg(&sc.nodes[node * 4 + 2]);
+        const float4 bx = __ldg(&sc.nodes[node * 4 + 0]);
+        const float4 by = __ldg(&sc.nodes[node * 4 + 1]);
+        const float4 bz = __ldg(&sc.nodes[node * 4 + 2]);
         refs = __ldg(reinterpret_cast<const int4 *>(&sc.nodes[node * 4 + 3]));
+        if (COUNT) n_box += 2;
+        float lx0 = fmaf(bx.x, t.inv.x, t.oinv.x), lx1 = fmaf(bx.y, t.inv.x, t.oinv.x);
+        float ly0 = fmaf(by.x, t.inv.y, t.oinv.y), ly1 = fmaf(by.y, t.inv.y, t.oinv.y);
+        float lz0 = fmaf(bz.x, t.inv.z, t.oinv.z), lz1 = fmaf(bz.y, t.inv.z, t.oinv.z);
+        ln = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), tmin));
+        lf = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), t.best.t));
+        float rx0 = fmaf(bx.z, t.inv.x, t.oinv.x), rx1 = fmaf(bx.w, t.inv.x, t.oinv.x);
+        float ry0 = fmaf(by.z, t.inv.y, t.oinv.y), ry1 = fmaf(by.w, t.inv.y, t.oinv.y);
+        float rz0 = fmaf(bz.z, t.inv.z, t.oinv.z), rz1 = fmaf(bz.w, t.inv.z, t.oinv.z);
+        rn = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), tmin));
+        rf = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), t.best.t));
     }
-    if (COUNT) n_box += 2;
-    float lx0 = fmaf(bx.x, t.inv.x, t.oinv.x), lx1 = fmaf(bx.y, t.inv.x, t.oinv.x);
-    float ly0 = fmaf(by.x, t.inv.y, t.oinv.y), ly1 = fmaf(by.y, t.inv.y, t.oinv.y);
-    float lz0 = fmaf(bz.x, t.inv.z, t.oinv.z), lz1 = fmaf(bz.y, t.inv.z, t.oinv.z);
-    float ln = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), tmin));
-    float lf = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), t.best.t));
-    float rx0 = fmaf(bx.z, t.inv.x, t.oinv.x), rx1 = fmaf(bx.w, t.inv.x, t.oinv.x);
-    float ry0 = fmaf(by.z, t.inv.y, t.oinv.y), ry1 = fmaf(by.w, t.inv.y, t.oinv.y);
-    float rz0 = fmaf(bz.z, t.inv.z, t.oinv.z), rz1 = fmaf(bz.w, t.inv.z, t.oinv.z);
-    float rn = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), tmin));
-    float rf = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), t.best.t));
     const bool hl = ln <= lf * kSlack;
     const bool hr = rn <= rf * kSlack;
     // Successor selection with predication instead of nested branches (this tail was 17 % of all executed instructions at
@@ -424,7 +441,7 @@ __device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, int3
     const bool rightNear = hr & (!hl | (rn < ln));
     const int32_t nearRef = rightNear ? refs.y : refs.x;
     const int32_t farRef = rightNear ? refs.x : refs.y;
-    const bool holdNear = any & (nearRef < 0) & (t.leaf_left == 0);  // reached a leaf and the slot is free: hold it
+    const bool holdNear = any & (nearRef < 0) & !trav_leaf_held(t);  // reached a leaf and the slot is free: hold it
     const bool needPush = both & !holdNear;
     const bool needPop = !any | (holdNear & !both);
     int32_t next = holdNear ? farRef : nearRef;
@@ -433,7 +450,7 @@ __device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, int3
     t.sp -= needPop ? 1 : 0;
     if (needPop) next = stack[t.sp];
     if (holdNear) trav_hold_leaf(t, nearRef);
-    if (next < 0 && next != kTravDone && t.leaf_left == 0) {  // the successor is itself a leaf and the slot is (still) free
+    if (next < 0 && next != kTravDone && !trav_leaf_held(t)) {  // the successor is itself a leaf and the slot is (still) free
         trav_hold_leaf(t, next);
         next = trav_pop(t, stack);
     }
@@ -479,17 +496,17 @@ __device__ __forceinline__ void trav_node_step4(const DevScene &sc, Trav &t, int
     int32_t next = PT_REF4(s0);
 #undef PT_REF4
     if (s0 == 0xffffffffu) next = trav_pop(t, stack);
-    if (next < 0 && next != kTravDone && t.leaf_left == 0) {  // a leaf and the slot is free: hold it, continue elsewhere
+    if (next < 0 && next != kTravDone && !trav_leaf_held(t)) {  // a leaf and the slot is free: hold it, continue elsewhere
         trav_hold_leaf(t, next);
         next = trav_pop(t, stack);
     }
     t.cur = next;
 }
 
-// one primitive of the held leaf (precondition: t.leaf_left > 0)
+// one primitive of the held leaf (precondition: trav_leaf_held(t))
 template <bool SPHERES, bool COUNT>
 __device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, int32_t *stack, float3 o, float3 d, float tmin, uint32_t &n_tri) {
-    const int32_t k = t.leaf_next;
+    const int32_t k = t.leaf >> 4;
     const float4 q0 = __ldg(&sc.prims[k * 3 + 0]);
     const float4 q1 = __ldg(&sc.prims[k * 3 + 1]);
     const float4 q2 = __ldg(&sc.prims[k * 3 + 2]);
@@ -510,9 +527,8 @@ __device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, int3
             t.best.prim = k;
         }
     }
-    t.leaf_next = k + 1;
-    t.leaf_left -= 1;
-    if (t.leaf_left == 0 && t.cur < 0 && t.cur != kTravDone) {  // a second leaf was waiting in `cur`
+    t.leaf += 15;  // position + 1, primitives left - 1
+    if (!trav_leaf_held(t) && t.cur < 0 && t.cur != kTravDone) {  // a second leaf was waiting in `cur`
         trav_hold_leaf(t, t.cur);
         t.cur = trav_pop(t, stack);
     }

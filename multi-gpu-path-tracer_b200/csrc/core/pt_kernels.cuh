@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __
         const int wait_for = min(refill_at, max(1, (n_paths * 3) >> 2));
         for (;;) {
             const bool can_node = tr.cur >= 0;
-            const bool can_prim = tr.leaf_left > 0;
+            const bool can_prim = trav_leaf_held(tr);
             const unsigned m_node = __ballot_sync(kFullMask, can_node);
             const unsigned m_prim = __ballot_sync(kFullMask, can_prim);
             const int n_active = __popc(m_node | m_prim);

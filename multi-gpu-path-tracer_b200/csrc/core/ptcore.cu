@@ -361,7 +361,7 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
     if ((sc->n_tris && (!sc->tri_pos || !sc->tri_mat)) || (sc->n_spheres && (!sc->sph || !sc->sph_mat)) || !sc->mats || (sc->n_tex && !sc->tex))
         return fail(h, PT_ERR_INVALID_ARGUMENT, "scene arrays missing");
     const int64_t n_prims = (int64_t)sc->n_tris + sc->n_spheres;
-    if (n_prims >= (1 << 28)) return fail(h, PT_ERR_UNSUPPORTED, "too many primitives for the leaf reference encoding");
+    if (n_prims >= (1 << 27)) return fail(h, PT_ERR_UNSUPPORTED, "too many primitives for the leaf reference encoding");
     for (int32_t i = 0; i < sc->n_tris; i++)
         if (sc->tri_mat[i] < 0 || sc->tri_mat[i] >= sc->n_mats) return fail(h, PT_ERR_INVALID_ARGUMENT, "triangle material index out of range");
     for (int32_t i = 0; i < sc->n_spheres; i++)
@@ -805,7 +805,7 @@ int pt_bvh_selftest(const PtSceneDesc *sc, int32_t leaf_max, PtStats *out, char 
     int max_leaf = 0;
     for (const FlatNode &n : bvh.nodes)
         for (int32_t ref : {n.left, n.right})
-            if (ref < 0) max_leaf = std::max(max_leaf, (int)((~ref) & (kMaxLeafPrims - 1)) + 1);
+            if (ref < 0) max_leaf = std::max(max_leaf, (int)leaf_count(ref));
     if (why[0] == 0 && !pb.empty() && max_leaf > std::max(1, std::min((int)opt.leaf_max, kMaxLeafPrims))) {
         if (msg && msg_len) snprintf(msg, msg_len, "leaf with %d primitives exceeds leaf_max", max_leaf);
         return PT_ERR_SYSTEM;
