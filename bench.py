@@ -399,7 +399,7 @@ def main():
                     "frac": abytes / (kernel_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
                     "traffic": ncu_traffic_bytes() if (world == 1 and spp == SPP and args.kernel == "persistent") else None, "algorithmic_bytes_per_launch": abytes, "kernel": {"persistent": "pt_wavefront_kernel", "direct": "pt_direct_kernel", "lockstep": "pt_persistent_kernel"}[args.kernel],
                     "peak_source": peaks["source"], "algorithmic_bytes_per_ray": BYTES_PER_RAY(per_ray["box"], per_ray["tri"]),
-                    "note": "algorithmic bytes (SURVEY 8d: 32 B per box test, 48 B per triangle test) are node/triangle fetches served by L1/L2 on this 1.5 MB scene; the kernel's own limiter is the ALU pipe (compare / min-max / select / permute instructions, 69 % busy in profiles/r01_ncu_wavefront_final_*.txt), see DESIGN.md 4.1",
+                    "note": "algorithmic bytes (SURVEY 8d: 32 B per box test, 48 B per triangle test) are node/triangle fetches served by L1/L2 on this 1.5 MB scene; the kernel's own limiter is the ALU pipe (compare / min-max / select / permute instructions, 61 % busy at 75 % issue utilisation in profiles/r01_ncu_wavefront_final_*.txt), see DESIGN.md 4.1",
                     "nodes": ("32-byte quantised" if (args.node_format == 2 or (args.node_format == 0 and 0 < st_build.get("quant_inflation", 0) <= 1.3)) else "64-byte float") if args.kernel == "persistent" and not args.bvh_width == 4 else "64-byte float"}
         roofline_fp32 = {"bound": "fp32", "achieved": aflops / (kernel_ms / 1e3) / 1e12, "peak": fp32_peak_max, "unit": "TFLOP/s",
                          "frac": aflops / (kernel_ms / 1e3) / 1e12 / fp32_peak_max, "peak_at_sustained_clock": 148 * 128 * 2 * sm_mhz * 1e6 / 1e12,
