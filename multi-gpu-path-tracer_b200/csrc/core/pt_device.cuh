@@ -534,6 +534,40 @@ __device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, int3
     }
 }
 
+// up to two primitives of the held leaf in one step (triangle-only scenes): the two tests are independent instruction streams
+// (a lane's chain of dependent instructions is what bounds the kernel, the FMA pipe is mostly idle), the two acceptances then
+// happen in leaf order, exactly as two single steps would
+template <bool COUNT>
+__device__ __forceinline__ void trav_prim_step2(const DevScene &sc, Trav &t, int32_t *stack, float3 o, float3 d, float tmin, uint32_t &n_tri) {
+    const int32_t k = t.leaf >> 4;
+    const bool two = (t.leaf & 15) >= 2;
+    const int32_t k1 = two ? k + 1 : k;
+    const float4 a0 = __ldg(&sc.prims[k * 3 + 0]), a1 = __ldg(&sc.prims[k * 3 + 1]), a2 = __ldg(&sc.prims[k * 3 + 2]);
+    const float4 b0 = __ldg(&sc.prims[k1 * 3 + 0]), b1 = __ldg(&sc.prims[k1 * 3 + 1]), b2 = __ldg(&sc.prims[k1 * 3 + 2]);
+    if (COUNT) n_tri += two ? 2 : 1;
+    float ta, ua, va, tb, ub, vb;
+    // range test against (tmin, +inf): the comparison with the current closest hit follows, in order
+    const bool oka = triangle_test(f3(a0.x, a0.y, a0.z), f3(a0.w, a1.x, a1.y), f3(a1.z, a1.w, a2.x), o, d, tmin, FLT_MAX, ta, ua, va);
+    const bool okb = triangle_test(f3(b0.x, b0.y, b0.z), f3(b0.w, b1.x, b1.y), f3(b1.z, b1.w, b2.x), o, d, tmin, FLT_MAX, tb, ub, vb) & two;
+    if (oka & ((ta < t.best.t) | ((ta == t.best.t) & (k < t.best.prim)))) {
+        t.best.t = ta;
+        t.best.u = ua;
+        t.best.v = va;
+        t.best.prim = k;
+    }
+    if (okb & ((tb < t.best.t) | ((tb == t.best.t) & (k1 < t.best.prim)))) {
+        t.best.t = tb;
+        t.best.u = ub;
+        t.best.v = vb;
+        t.best.prim = k1;
+    }
+    t.leaf += two ? 30 : 15;
+    if (!trav_leaf_held(t) && t.cur < 0 && t.cur != kTravDone) {  // a second leaf was waiting in `cur`
+        trav_hold_leaf(t, t.cur);
+        t.cur = trav_pop(t, stack);
+    }
+}
+
 // ----------------------------------------------------------------------------------------
 // shading pieces
 // ----------------------------------------------------------------------------------------

@@ -269,7 +269,10 @@ __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __
                         }
                 }
             } else {
-                if (can_prim) trav_prim_step<SPHERES, COUNT>(p.scene, tr, stack, ro, rd, 0.001f, n_tri);
+                if (can_prim) {
+                    if (SPHERES) trav_prim_step<SPHERES, COUNT>(p.scene, tr, stack, ro, rd, 0.001f, n_tri);
+                    else trav_prim_step2<COUNT>(p.scene, tr, stack, ro, rd, 0.001f, n_tri);
+                }
             }
         }
 
