@@ -192,6 +192,10 @@ int ptcore_debug_trace_pixel(ptcore_t *h, uint32_t width, uint32_t height, int32
  * validates it (every primitive in exactly one leaf, child boxes inside parents and around their primitives, references in
  * range, depth within the device stack, leaves <= leaf_max).  Needs no GPU.  msg receives the reason on failure. */
 int pt_bvh_selftest(const PtSceneDesc *scene, int32_t leaf_max, PtStats *out, char *msg, size_t msg_len);
+/* Host emulation of the kernel's two slab tests (float planes / quantised planes) on pseudo-random rays against the boxes of
+ * the scene's tree: a box accepted on float planes must be accepted on quantised planes.
+ * counts = {box tests, accepted on float planes, accepted on quantised planes}.  No GPU needed. */
+int pt_quant_selftest(const PtSceneDesc *scene, uint32_t n_rays, uint32_t seed, uint64_t counts[3], char *msg, size_t msg_len);
 
 /* ---- multi-GPU plumbing: a tile counter shared by the ranks of one node (POSIX shared memory).
  *      Replaces the per-frame static rectangles of RenderManager/TaskGenerator

@@ -518,6 +518,100 @@ const char *validate_quantised(const std::vector<FlatNode> &nodes, const std::ve
     return "";
 }
 
+namespace {
+struct Lcg {
+    uint64_t s;
+    uint32_t next() {
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        return (uint32_t)(s >> 32);
+    }
+    float unit() { return (float)(next() >> 8) * (1.0f / 16777216.0f); }
+};
+inline float slab_inv1(float d) {  // slab_inverse, pt_device.cuh
+    const float kTiny = 8.271806125530277e-25f;
+    const float c = std::fabs(d) < kTiny ? std::copysign(kTiny, d) : d;
+    return 1.0f / c;
+}
+}  // namespace
+
+const char *check_quantised_walk(const std::vector<FlatNode> &nodes, const std::vector<QuantNode> &q, const QuantGrid &g, uint32_t n_rays, uint32_t seed,
+                                 uint32_t max_nodes, uint64_t counts[3]) {
+    counts[0] = counts[1] = counts[2] = 0;
+    if (nodes.empty() || q.size() != nodes.size()) return "no nodes";
+    const float kSlack = 1.0000004f, tmin = 0.001f;
+    Lcg rng{0x9e3779b97f4a7c15ull ^ seed};
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; k++) {
+        lo[k] = g.lo[k];
+        hi[k] = g.lo[k] + 32767.0f / g.scale[k];
+    }
+    const size_t stride = std::max<size_t>(1, nodes.size() / std::max<uint32_t>(1, max_nodes));
+    for (uint32_t r = 0; r < n_rays; r++) {
+        float o[3], d[3];
+        const uint32_t kind = rng.next() % 10;
+        const size_t pickIdx = rng.next() % nodes.size();
+        const FlatNode &pick = nodes[pickIdx];
+        for (int k = 0; k < 3; k++) {
+            const float ext = hi[k] - lo[k];
+            o[k] = lo[k] - 0.25f * ext + 1.5f * ext * rng.unit();
+            d[k] = 2.0f * rng.unit() - 1.0f;
+        }
+        if (kind == 1) o[rng.next() % 3] = pick.bx[rng.next() % 4];                       // origin coordinate taken from a box plane
+        if (kind == 2) { o[0] = pick.bx[0]; o[1] = pick.by[1]; o[2] = pick.bz[2]; }          // origin on a box corner
+        if (kind == 3) d[rng.next() % 3] = 0.0f;                                            // axis-parallel in one component
+        if (kind == 4) { int a = rng.next() % 3; d[(a + 1) % 3] = 0.0f; d[(a + 2) % 3] = -0.0f; }  // axis-parallel ray
+        if (kind == 5) d[rng.next() % 3] = 1e-30f * (rng.unit() - 0.5f);                    // tiny component (clamped by slab_inverse)
+        if (kind == 6) for (int k = 0; k < 3; k++) d[k] *= 1000.0f;                         // long unnormalised direction (light sampling)
+        if (kind >= 7 && pick.bx[0] <= pick.bx[1]) {                                        // aimed at the picked node's left box: inside, on a face, on an edge
+            const float *pb3[3] = {pick.bx, pick.by, pick.bz};
+            for (int k = 0; k < 3; k++) {
+                const uint32_t where = kind == 7 ? 2u : rng.next() % 3;                       // 0 = min plane, 1 = max plane, 2 = inside
+                const float target = where == 0 ? pb3[k][0] : where == 1 ? pb3[k][1] : pb3[k][0] + (pb3[k][1] - pb3[k][0]) * rng.unit();
+                d[k] = target - o[k];
+            }
+        }
+        const float best = (rng.next() & 1) ? FLT_MAX : 4000.0f * rng.unit();
+        // float planes: t = b * inv + (-o * inv)
+        float inv[3], oinv[3], ginv[3], goinv[3];
+        bool gneg[3];
+        for (int k = 0; k < 3; k++) {
+            inv[k] = slab_inv1(d[k]);
+            oinv[k] = -o[k] * inv[k];
+            const float og = (o[k] - g.lo[k]) * g.scale[k];
+            ginv[k] = slab_inv1(d[k] * g.scale[k]);
+            goinv[k] = -(32768.0f + og) * ginv[k];
+            gneg[k] = ginv[k] < 0.f;
+        }
+        auto test_node = [&](size_t i) -> bool {
+            const FlatNode &n = nodes[i];
+            const float *fb[3] = {n.bx, n.by, n.bz};
+            const uint32_t qb[3][2] = {{q[i].lx, q[i].rx}, {q[i].ly, q[i].ry}, {q[i].lz, q[i].rz}};
+            for (int side = 0; side < 2; side++) {
+                if (!(n.bx[side * 2] <= n.bx[side * 2 + 1])) continue;
+                float tn = tmin, tf = best, qn = tmin, qf = best;
+                for (int k = 0; k < 3; k++) {
+                    const float t0 = std::fmaf(fb[k][side * 2], inv[k], oinv[k]), t1 = std::fmaf(fb[k][side * 2 + 1], inv[k], oinv[k]);
+                    tn = std::fmax(tn, std::fmin(t0, t1));
+                    tf = std::fmin(tf, std::fmax(t0, t1));
+                    const float plo = 32768.0f + (float)(qb[k][side] & 0xffffu), phi = 32768.0f + (float)(qb[k][side] >> 16);
+                    qn = std::fmax(qn, std::fmaf(gneg[k] ? phi : plo, ginv[k], goinv[k]));
+                    qf = std::fmin(qf, std::fmaf(gneg[k] ? plo : phi, ginv[k], goinv[k]));
+                }
+                const bool hf = tn <= tf * kSlack, hq = qn <= qf * kSlack;
+                counts[0]++;
+                counts[1] += hf;
+                counts[2] += hq;
+                if (hf && !hq) return false;
+            }
+            return true;
+        };
+        bool ok = test_node(pickIdx);  // the node the ray was aimed at, then a strided sample of all nodes
+        for (size_t i = (size_t)(rng.next() % stride); ok && i < nodes.size(); i += stride) ok = test_node(i);
+        if (!ok) return "a box accepted on float planes was rejected on quantised planes";
+    }
+    return "";
+}
+
 const char *validate_bvh(const BvhBuildResult &bvh, const std::vector<PrimBounds> &bounds) {
     const size_t n = bounds.size();
     if (bvh.nodes.empty()) return "no nodes";

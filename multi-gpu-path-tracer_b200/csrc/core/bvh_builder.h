@@ -99,6 +99,13 @@ QuantGrid quantise_nodes(const std::vector<FlatNode> &nodes, std::vector<QuantNo
 // quantised box / surface area of the float box), the price of the coarser planes.  Returns "" if valid.
 const char *validate_quantised(const std::vector<FlatNode> &nodes, const std::vector<QuantNode> &q, const QuantGrid &g, double *inflation);
 
+// Host emulation (same float operations, fmaf where the kernel uses fma) of the two slab tests of trav_node_step on `n_rays`
+// pseudo-random rays — origins inside and outside the scene, on box planes, directions with zero / tiny / axis-parallel
+// components, finite and infinite far limits — against every child box of up to `max_nodes` nodes: a box accepted on float
+// planes must be accepted on quantised planes.  counts = {tests, accepted on float planes, accepted on quantised planes}.
+const char *check_quantised_walk(const std::vector<FlatNode> &nodes, const std::vector<QuantNode> &q, const QuantGrid &g, uint32_t n_rays, uint32_t seed,
+                                 uint32_t max_nodes, uint64_t counts[3]);
+
 // Structural validation used by the tests: every primitive in exactly one leaf, child boxes
 // enclose their primitives, refs in range, depth within the device stack. Returns "" if valid.
 const char *validate_bvh(const BvhBuildResult &bvh, const std::vector<PrimBounds> &bounds);

@@ -258,3 +258,14 @@ def test_gpu_monitor_accumulators_and_wire_format_without_a_gpu(core_lib):
     assert exe.exists(), "run __graft_entry__.build()"
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "GPU_MONITOR_TEST_OK" in r.stdout, r.stdout
+
+
+def test_quantised_planes_never_reject_what_float_planes_accept(ptb, core_lib, duck):
+    """Host emulation of trav_node_step's two slab tests (same float operations) on pseudo-random rays — aimed at boxes, on their
+    faces and edges, axis-parallel, tiny components, finite far limits — against the trees of three scenes."""
+    field, _ = ptb.scenes.rtow_sphere_field()
+    mesh = ptb.scenes.displaced_sphere_in_cornell(duck, n=60)
+    for scene, rays, seed in ((duck, 1500, 1), (field, 2000, 2), (mesh, 800, 3)):
+        ok, msg, (tests, on_float, on_quant) = ptb.quant_selftest(scene, rays, seed)
+        assert ok, msg
+        assert tests > 1_000_000 and on_float > 5_000 and on_quant >= on_float, (tests, on_float, on_quant)
