@@ -188,10 +188,7 @@ public:
     }
 
 private:
-    static bool sameCamera(const CameraConfig &a, const CameraConfig &b) {
-        return a.front.x == b.front.x && a.front.y == b.front.y && a.front.z == b.front.z && a.lookFrom.x == b.lookFrom.x && a.lookFrom.y == b.lookFrom.y &&
-               a.lookFrom.z == b.lookFrom.z && a.vfov == b.vfov && a.hfov == b.hfov;
-    }
+    static bool sameCamera(const CameraConfig &a, const CameraConfig &b) { return a.sameViewAs(b); }
     void uploadCamera() {
         CameraConfig snap = cameraConfig_;
         PtCamera c{{snap.lookFrom.x, snap.lookFrom.y, snap.lookFrom.z}, {snap.front.x, snap.front.y, snap.front.z}, snap.vfov, snap.hfov};
