@@ -85,7 +85,7 @@ def test_monitor_thread_reports_nvml_figures_and_render_times(tmp_path, duck_fil
     r = subprocess.run([str(mon)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "GPU_MONITOR_TEST_OK" in r.stdout and "nvml available: 1" in r.stdout, r.stdout[-800:]
     out = tmp_path / "m.ppm"
-    r = subprocess.run([str(CLI), "7", str(duck_file), "--out", str(out), *map(str, ("--width", 640, "--height", 360, "--spp", 256, "--depth", 10, "--frames", 40, "--monitor", 1))],
+    r = subprocess.run([str(CLI), "7", str(duck_file), "--out", str(out), *map(str, ("--width", 640, "--height", 360, "--spp", 256, "--depth", 10, "--frames", 100, "--monitor", 1))],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-500:]
     msgs = [ln for ln in r.stdout.splitlines() if ln.startswith("RENDER_STATS#")]
