@@ -107,7 +107,8 @@ enum { /* ptcore_set_option keys */
     PT_OPT_NODE_BURST = 7,   /* wavefront kernel: node steps per warp vote (1..4) */
     PT_OPT_MIN_BLOCKS = 8,   /* accepted for compatibility: only the __launch_bounds__(128, 8) (64-register) build is shipped */
     PT_OPT_BVH_WIDTH = 9,    /* wavefront kernel: walk the 2-wide (64 B nodes, default) or the collapsed 4-wide (128 B nodes) tree; 4-wide measured 20 % slower on cornell_duck */
-    PT_OPT_NODE_FORMAT = 10  /* wavefront kernel, 2-wide tree: PT_NODES_* */
+    PT_OPT_NODE_FORMAT = 10, /* wavefront kernel, 2-wide tree: PT_NODES_* */
+    PT_OPT_SAH_INTERSECT_COST = 11 /* next ptcore_upload_scene: cost of one primitive test relative to one node visit, in hundredths (default 120) */
 };
 enum {
     PT_NODES_AUTO = 0,       /* default: quantised when PtStats.quant_inflation <= 1.3, else full */

@@ -24,6 +24,7 @@ PT_MAT_LAMBERTIAN, PT_MAT_METAL, PT_MAT_DIELECTRIC, PT_MAT_DIFFUSE_LIGHT, PT_MAT
 PT_OPT_KERNEL, PT_OPT_COUNT_TESTS, PT_OPT_BVH_LEAF_MAX, PT_OPT_BLOCKS_PER_SM, _PT_OPT_RESERVED_5, PT_OPT_REFILL_AT, PT_OPT_NODE_BURST, PT_OPT_MIN_BLOCKS, PT_OPT_BVH_WIDTH = range(1, 10)
 PT_KERNEL_PERSISTENT, PT_KERNEL_DIRECT, PT_KERNEL_LOCKSTEP = 0, 1, 2
 PT_OPT_NODE_FORMAT = 10
+PT_OPT_SAH_INTERSECT_COST = 11
 PT_NODES_AUTO, PT_NODES_FULL, PT_NODES_QUANTISED = 0, 1, 2
 
 

@@ -73,6 +73,7 @@ struct ptcore {
     int min_blocks = 8;
     int bvh_width = 2;
     int node_format = PT_NODES_AUTO;
+    int sah_isect_x100 = 120;
     bool trace_steps = false;
     uint32_t *ident_blocks = nullptr;
     uint32_t ident_blocks_n = 0;
@@ -378,6 +379,7 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
 
     BvhBuildOptions opt;
     opt.leaf_max = h->leaf_max;
+    opt.intersect_cost = (float)h->sah_isect_x100 / 100.0f;
     BvhBuildResult bvh = build_bvh(pb, opt);
 
     // ---- lights: DevicePathTracer.h:302-307 (emissiveFactor channel > 0.0001, scene order) ----
@@ -607,6 +609,10 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
         case PT_OPT_BVH_WIDTH:
             if (value != 2 && value != 4) return fail(h, PT_ERR_INVALID_ARGUMENT, "bvh_width must be 2 or 4");
             h->bvh_width = (int)value;
+            return PT_OK;
+        case PT_OPT_SAH_INTERSECT_COST:
+            if (value < 10 || value > 1000) return fail(h, PT_ERR_INVALID_ARGUMENT, "sah intersect cost must be in [10, 1000] hundredths");
+            h->sah_isect_x100 = (int)value;
             return PT_OK;
         case PT_OPT_NODE_FORMAT:
             if (value != PT_NODES_AUTO && value != PT_NODES_FULL && value != PT_NODES_QUANTISED) return fail(h, PT_ERR_INVALID_ARGUMENT, "unknown node format");
