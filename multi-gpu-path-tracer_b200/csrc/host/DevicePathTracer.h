@@ -19,6 +19,7 @@
 
 #include "../../../include/ptcore.h"
 #include "CameraConfig.h"
+#include "RenderTask.h"
 #include "Framebuffer.h"
 #include "HostScene.h"
 #include "RendererConfig.h"
@@ -29,13 +30,6 @@
 #include <mutex>
 #include <vector>
 
-struct RenderTask {
-    int width;
-    int height;
-    int offset_x;
-    int offset_y;
-    int time = 0;
-};
 
 class DevicePathTracer {
 public:

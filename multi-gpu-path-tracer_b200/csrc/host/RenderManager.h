@@ -318,119 +318,14 @@ private:
         }
     }
 
-    // DSFL (reference :334-408, :546-639): keep the layout, move every border by at most one thread block per frame
-    // towards the position that would have equalised the previous frame's task times.
+    // DSFL / DSDL: the arithmetic lives in TaskGenerator (pure functions of the previous frame's task times)
     void adjustTasksDSFL() {
-        const int W = (int)config_.resolution.width, H = (int)config_.resolution.height;
-        const int bx = (int)std::max(1u, config_.threadBlockSize.x), by = (int)std::max(1u, config_.threadBlockSize.y);
-        // columns inside each row
-        for (auto &row : taskLayout_) {
-            double total = 0;
-            for (int id : row) total += std::max(1, renderTasks_[(size_t)id].time);
-            double acc = 0;
-            int x = 0;
-            for (size_t c = 0; c + 1 < row.size(); c++) {
-                RenderTask &t = renderTasks_[(size_t)row[c]];
-                // where the border should be so that this column takes total/n: scale the column by target/actual time
-                double target = total / (double)row.size();
-                int ideal = (int)std::lround(t.width * target / std::max(1, t.time));
-                int step = std::clamp(ideal - t.width, -bx, bx);
-                int remainingCols = (int)(row.size() - 1 - c);
-                int nw = std::clamp(t.width + step, 1, W - x - remainingCols);
-                t.offset_x = x;
-                t.width = nw;
-                x += nw;
-                acc += target;
-            }
-            RenderTask &last = renderTasks_[(size_t)row.back()];
-            last.offset_x = x;
-            last.width = W - x;
-        }
-        // row heights
-        std::vector<double> rowTime;
-        double total = 0;
-        for (auto &row : taskLayout_) {
-            double s = 0;
-            for (int id : row) s += std::max(1, renderTasks_[(size_t)id].time);
-            rowTime.push_back(s);
-            total += s;
-        }
-        int y = 0;
-        for (size_t r = 0; r < taskLayout_.size(); r++) {
-            int hgt;
-            int cur = renderTasks_[(size_t)taskLayout_[r][0]].height;
-            if (r + 1 < taskLayout_.size()) {
-                double target = total / (double)taskLayout_.size();
-                int ideal = (int)std::lround(cur * target / std::max(1.0, rowTime[r]));
-                int step = std::clamp(ideal - cur, -by, by);
-                hgt = std::clamp(cur + step, 1, H - y - (int)(taskLayout_.size() - 1 - r));
-            } else {
-                hgt = H - y;
-            }
-            for (int id : taskLayout_[r]) {
-                renderTasks_[(size_t)id].offset_y = y;
-                renderTasks_[(size_t)id].height = hgt;
-            }
-            y += hgt;
-        }
+        taskGen_.adjustTasksDSFL(renderTasks_, taskLayout_, (int)config_.resolution.width, (int)config_.resolution.height,
+                                 (int)std::max(1u, config_.threadBlockSize.x), (int)std::max(1u, config_.threadBlockSize.y));
     }
-
-    // DSDL (reference :264-331): spread each task's time over the thread blocks it covered, then bisect the block grid
-    // recursively (alternating axis) at the time-weighted median until there is one rectangle per worker.
     void adjustTasksDSDL() {
-        const int W = (int)config_.resolution.width, H = (int)config_.resolution.height;
-        const int bx = (int)std::max(1u, config_.threadBlockSize.x), by = (int)std::max(1u, config_.threadBlockSize.y);
-        const int gw = (W + bx - 1) / bx, gh = (H + by - 1) / by;
-        std::vector<float> cost((size_t)gw * gh, 0.f);
-        for (const RenderTask &t : renderTasks_) {
-            int x0 = t.offset_x / bx, x1 = std::min(gw, (t.offset_x + t.width + bx - 1) / bx);
-            int y0 = t.offset_y / by, y1 = std::min(gh, (t.offset_y + t.height + by - 1) / by);
-            int n = std::max(1, (x1 - x0) * (y1 - y0));
-            for (int yy = y0; yy < y1; yy++)
-                for (int xx = x0; xx < x1; xx++) cost[(size_t)yy * gw + xx] += (float)std::max(1, t.time) / (float)n;
-        }
-        std::vector<RenderTask> out;
-        struct Rect { int x0, y0, x1, y1, count; bool vert; };
-        std::vector<Rect> stack{{0, 0, gw, gh, threadCount_, true}};
-        while (!stack.empty()) {
-            Rect r = stack.back();
-            stack.pop_back();
-            if (r.count <= 1) {
-                int px0 = r.x0 * bx, py0 = r.y0 * by, px1 = std::min(W, r.x1 * bx), py1 = std::min(H, r.y1 * by);
-                out.push_back({px1 - px0, py1 - py0, px0, py0});
-                continue;
-            }
-            const int left = r.count / 2;
-            double total = 0;
-            for (int yy = r.y0; yy < r.y1; yy++)
-                for (int xx = r.x0; xx < r.x1; xx++) total += cost[(size_t)yy * gw + xx];
-            const double target = total * (double)left / (double)r.count;
-            bool vert = r.vert;
-            if (vert && r.y1 - r.y0 < 2) vert = false;
-            if (!vert && r.x1 - r.x0 < 2) vert = true;
-            double acc = 0;
-            if (vert) {
-                int cut = r.y0 + 1;
-                for (int yy = r.y0; yy < r.y1 - 1; yy++) {
-                    for (int xx = r.x0; xx < r.x1; xx++) acc += cost[(size_t)yy * gw + xx];
-                    cut = yy + 1;
-                    if (acc >= target) break;
-                }
-                stack.push_back({r.x0, cut, r.x1, r.y1, r.count - left, false});
-                stack.push_back({r.x0, r.y0, r.x1, cut, left, false});
-            } else {
-                int cut = r.x0 + 1;
-                for (int xx = r.x0; xx < r.x1 - 1; xx++) {
-                    for (int yy = r.y0; yy < r.y1; yy++) acc += cost[(size_t)yy * gw + xx];
-                    cut = xx + 1;
-                    if (acc >= target) break;
-                }
-                stack.push_back({cut, r.y0, r.x1, r.y1, r.count - left, true});
-                stack.push_back({r.x0, r.y0, cut, r.y1, left, true});
-            }
-        }
-        out.resize((size_t)threadCount_, RenderTask{0, 0, 0, 0});
-        renderTasks_ = out;
+        renderTasks_ = taskGen_.bisectTasksDSDL(renderTasks_, threadCount_, (int)config_.resolution.width, (int)config_.resolution.height,
+                                                (int)std::max(1u, config_.threadBlockSize.x), (int)std::max(1u, config_.threadBlockSize.y));
     }
 
     std::vector<std::shared_ptr<DevicePathTracer>> devicePathTracers_{};

@@ -1,11 +1,15 @@
 // TaskGenerator.h — image -> RenderTask rectangles.
 // generateEqualTasks keeps the reference's results (src/Scheduling/TaskGenerator.h:46-55,58-80: equal columns, or
 // equal cells laid out by `taskLayout` with the last column/row absorbing the remainder); generateTiles is the
-// fine-grained grid the DYNAMIC scheduler hands out one claim at a time.
+// fine-grained grid the DYNAMIC scheduler hands out one claim at a time; adjustTasksDSFL / bisectTasksDSDL are the two
+// time-driven schedulers of the reference (src/RenderManager.h:264-408, :546-639) as pure functions of the tasks and
+// their last render times, so they can be tested without a GPU (csrc/host/task_generator_test.cpp).
 #pragma once
 
-#include "DevicePathTracer.h"
+#include "RenderTask.h"
 
+#include <algorithm>
+#include <cmath>
 #include <vector>
 
 class TaskGenerator {
@@ -44,6 +48,115 @@ public:
         for (int y = 0; y < height; y += tileH)
             for (int x = 0; x < width; x += tileW) tiles.push_back({std::min(tileW, width - x), std::min(tileH, height - y), x, y});
         return tiles;
+    }
+
+    // DSFL: keep the layout, move every border by at most one thread block per frame towards the position that would have
+    // equalised the previous frame's task times (columns inside each row, then the row heights).
+    void adjustTasksDSFL(std::vector<RenderTask> &tasks, const std::vector<std::vector<int>> &layout, int W, int H, int bx, int by) {
+        for (const auto &row : layout) {
+            if (row.empty()) continue;
+            double total = 0;
+            for (int id : row) total += std::max(1, tasks[(size_t)id].time);
+            int x = 0;
+            for (size_t c = 0; c + 1 < row.size(); c++) {
+                RenderTask &t = tasks[(size_t)row[c]];
+                // where the border should be so that this column takes total/n: scale the column by target/actual time
+                double target = total / (double)row.size();
+                int ideal = (int)std::lround(t.width * target / std::max(1, t.time));
+                int step = std::clamp(ideal - t.width, -bx, bx);
+                int remainingCols = (int)(row.size() - 1 - c);
+                int nw = std::clamp(t.width + step, 1, std::max(1, W - x - remainingCols));
+                t.offset_x = x;
+                t.width = nw;
+                x += nw;
+            }
+            RenderTask &last = tasks[(size_t)row.back()];
+            last.offset_x = x;
+            last.width = W - x;
+        }
+        std::vector<double> rowTime;
+        double total = 0;
+        for (const auto &row : layout) {
+            double s = 0;
+            for (int id : row) s += std::max(1, tasks[(size_t)id].time);
+            rowTime.push_back(s);
+            total += s;
+        }
+        int y = 0;
+        for (size_t r = 0; r < layout.size(); r++) {
+            if (layout[r].empty()) continue;
+            int hgt;
+            int cur = tasks[(size_t)layout[r][0]].height;
+            if (r + 1 < layout.size()) {
+                double target = total / (double)layout.size();
+                int ideal = (int)std::lround(cur * target / std::max(1.0, rowTime[r]));
+                int step = std::clamp(ideal - cur, -by, by);
+                hgt = std::clamp(cur + step, 1, std::max(1, H - y - (int)(layout.size() - 1 - r)));
+            } else {
+                hgt = H - y;
+            }
+            for (int id : layout[r]) {
+                tasks[(size_t)id].offset_y = y;
+                tasks[(size_t)id].height = hgt;
+            }
+            y += hgt;
+        }
+    }
+
+    // DSDL: spread each task's time over the thread blocks it covered, then bisect the block grid recursively (alternating
+    // axis) at the time-weighted median until there is one rectangle per worker.
+    std::vector<RenderTask> bisectTasksDSDL(const std::vector<RenderTask> &tasks, int count, int W, int H, int bx, int by) {
+        const int gw = (W + bx - 1) / bx, gh = (H + by - 1) / by;
+        std::vector<float> cost((size_t)gw * gh, 0.f);
+        for (const RenderTask &t : tasks) {
+            int x0 = t.offset_x / bx, x1 = std::min(gw, (t.offset_x + t.width + bx - 1) / bx);
+            int y0 = t.offset_y / by, y1 = std::min(gh, (t.offset_y + t.height + by - 1) / by);
+            int n = std::max(1, (x1 - x0) * (y1 - y0));
+            for (int yy = y0; yy < y1; yy++)
+                for (int xx = x0; xx < x1; xx++) cost[(size_t)yy * gw + xx] += (float)std::max(1, t.time) / (float)n;
+        }
+        std::vector<RenderTask> out;
+        struct Rect { int x0, y0, x1, y1, count; bool vert; };
+        std::vector<Rect> stack{{0, 0, gw, gh, count, true}};
+        while (!stack.empty()) {
+            Rect r = stack.back();
+            stack.pop_back();
+            if (r.count <= 1 || (r.x1 - r.x0 < 2 && r.y1 - r.y0 < 2)) {  // one worker left, or a single block that cannot be cut
+                int px0 = r.x0 * bx, py0 = r.y0 * by, px1 = std::min(W, r.x1 * bx), py1 = std::min(H, r.y1 * by);
+                out.push_back({px1 - px0, py1 - py0, px0, py0});
+                continue;
+            }
+            const int left = r.count / 2;
+            double total = 0;
+            for (int yy = r.y0; yy < r.y1; yy++)
+                for (int xx = r.x0; xx < r.x1; xx++) total += cost[(size_t)yy * gw + xx];
+            const double target = total * (double)left / (double)r.count;
+            bool vert = r.vert;
+            if (vert && r.y1 - r.y0 < 2) vert = false;
+            if (!vert && r.x1 - r.x0 < 2) vert = true;
+            double acc = 0;
+            if (vert) {
+                int cut = r.y0 + 1;
+                for (int yy = r.y0; yy < r.y1 - 1; yy++) {
+                    for (int xx = r.x0; xx < r.x1; xx++) acc += cost[(size_t)yy * gw + xx];
+                    cut = yy + 1;
+                    if (acc >= target) break;
+                }
+                stack.push_back({r.x0, cut, r.x1, r.y1, r.count - left, false});
+                stack.push_back({r.x0, r.y0, r.x1, cut, left, false});
+            } else {
+                int cut = r.x0 + 1;
+                for (int xx = r.x0; xx < r.x1 - 1; xx++) {
+                    for (int yy = r.y0; yy < r.y1; yy++) acc += cost[(size_t)yy * gw + xx];
+                    cut = xx + 1;
+                    if (acc >= target) break;
+                }
+                stack.push_back({cut, r.y0, r.x1, r.y1, r.count - left, true});
+                stack.push_back({r.x0, r.y0, cut, r.y1, left, true});
+            }
+        }
+        out.resize((size_t)std::max(0, count), RenderTask{0, 0, 0, 0});  // workers beyond the number of blocks get empty tasks
+        return out;
     }
 
     void setRes(int width, int height) {

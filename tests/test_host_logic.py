@@ -269,3 +269,13 @@ def test_quantised_planes_never_reject_what_float_planes_accept(ptb, core_lib, d
         ok, msg, (tests, on_float, on_quant) = ptb.quant_selftest(scene, rays, seed)
         assert ok, msg
         assert tests > 1_000_000 and on_float > 5_000 and on_quant >= on_float, (tests, on_float, on_quant)
+
+
+def test_task_generator_and_time_driven_schedulers_tile_the_frame(core_lib):
+    """csrc/host/TaskGenerator.h: equal tasks, DYNAMIC tiles, DSFL border nudging (bounded steps, converges to the equal-time
+    border) and DSDL time-weighted bisection (reference src/RenderManager.h:264-408,546-639) — every result tiles the frame."""
+    import subprocess
+    exe = ROOT / "multi-gpu-path-tracer_b200" / "_lib" / "task_generator_test"
+    assert exe.exists(), "run __graft_entry__.build()"
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "TASK_GENERATOR_TEST_OK" in r.stdout, r.stdout[-800:]
