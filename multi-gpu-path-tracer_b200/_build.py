@@ -6,7 +6,7 @@ Outputs (git-ignored, shipped to the GPU box by gpurun):
     multi-gpu-path-tracer_b200/_lib/libptcore.so     the C ABI of include/ptcore.h (CUDA kernels, sm_100a)
     multi-gpu-path-tracer_b200/_lib/ptscene_tool     scene converter
     multi-gpu-path-tracer_b200/_lib/cuda_project     host executable mirroring the reference's CLI
-    multi-gpu-path-tracer_b200/_lib/host_api_test, gpu_monitor_test, task_generator_test   C++ tests of the host mirror
+    multi-gpu-path-tracer_b200/_lib/host_api_test, gpu_monitor_test, task_generator_test, argument_loader_test   C++ tests of the host mirror
 """
 from __future__ import annotations
 
@@ -96,6 +96,11 @@ def build_tools(force: bool = False, verbose: bool = False) -> None:
         exe = LIBDIR / "task_generator_test"
         if force or _stale(exe, [tg_src, CSRC / "host" / "TaskGenerator.h", CSRC / "host" / "RenderTask.h"]):
             _run([HOST_CXX, "-std=c++17", "-O2", tg_src, "-o", exe], verbose)
+    al_src = CSRC / "host" / "argument_loader_test.cpp"
+    if al_src.exists():
+        exe = LIBDIR / "argument_loader_test"
+        if force or _stale(exe, [al_src, CSRC / "host" / "ArgumentLoader.h", CSRC / "host" / "RendererConfig.h"]):
+            _run([HOST_CXX, "-std=c++17", "-O2", f"-I{CUDA_HOME}/include", al_src, "-o", exe], verbose)
     cli_src = CSRC / "host" / "main.cpp"
     if cli_src.exists():
         cli = LIBDIR / "cuda_project"

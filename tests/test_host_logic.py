@@ -279,3 +279,13 @@ def test_task_generator_and_time_driven_schedulers_tile_the_frame(core_lib):
     assert exe.exists(), "run __graft_entry__.build()"
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "TASK_GENERATOR_TEST_OK" in r.stdout, r.stdout[-800:]
+
+
+def test_argument_loader_positionals_flags_and_errors(core_lib):
+    """csrc/host/ArgumentLoader.h: the reference's two positionals with their defaults (src/ArgumentLoader.h:10-13), every added
+    flag, and exceptions that name the offending argument."""
+    import subprocess
+    exe = ROOT / "multi-gpu-path-tracer_b200" / "_lib" / "argument_loader_test"
+    assert exe.exists(), "run __graft_entry__.build()"
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "ARGUMENT_LOADER_TEST_OK" in r.stdout, r.stdout[-800:]
