@@ -212,11 +212,13 @@ def test_bvh_is_structurally_valid_for_fixtures_and_edge_cases(ptb, core_lib, du
         "all coincident": np.tile(rng.random((1, 9), dtype=np.float32), (37, 1)),
         "collinear centroids": np.stack([np.concatenate([[i, 0, 0], [i + .5, 0, 0], [i, .5, 0]]) for i in range(200)]).astype(np.float32),
         "huge range": (rng.random((500, 9), dtype=np.float32) * np.float32(1e6)) ** 2,
+        # exponentially spaced slivers: the SAH peels them off one by one; the builder must switch to median splits in time
+        "exponential spacing": np.stack([np.concatenate([[x, 0, 0], [x * 1.0001, 0, 0], [x, x * 0.0001, 0]]) for x in 1.02 ** np.arange(3000)]).astype(np.float32),
     }
     for name, pos in cases.items():
         sc = ptb.Scene(tri_pos=pos, tri_uv=np.zeros((len(pos), 6), np.float32), tri_mat=np.zeros(len(pos), np.int32), mats=mats)
         ok, msg, st = ptb.bvh_selftest(sc, 4)
-        assert ok, (name, msg)
+        assert ok and st["bvh_depth"] <= 48, (name, msg, st["bvh_depth"])
     sph = ptb.Scene(sph=np.array([[0, 0, 0, 1], [3, 0, 0, 0.5], [0, -1000, 0, 999]], np.float32), sph_mat=np.zeros(3, np.int32), mats=mats)
     ok, msg, st = ptb.bvh_selftest(sph, 4)
     assert ok, msg
