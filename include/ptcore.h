@@ -197,6 +197,11 @@ int pt_bvh_selftest(const PtSceneDesc *scene, int32_t leaf_max, PtStats *out, ch
  * the scene's tree: a box accepted on float planes must be accepted on quantised planes.
  * counts = {box tests, accepted on float planes, accepted on quantised planes}.  No GPU needed. */
 int pt_quant_selftest(const PtSceneDesc *scene, uint32_t n_rays, uint32_t seed, uint64_t counts[3], char *msg, size_t msg_len);
+/* Host restatement of the kernel's resumable walk (node steps with a held leaf and a sentinel stack, two-primitive leaf steps,
+ * tie rule) on the scene's triangles: for n_rays pseudo-random rays the closest hit of the walk over float planes, of the walk
+ * over quantised planes and of testing every triangle must coincide (same triangle, same t, u, v).
+ * counts = {rays, rays that hit, node steps on float planes, node steps on quantised planes}.  No GPU needed. */
+int pt_walk_selftest(const PtSceneDesc *scene, uint32_t n_rays, uint32_t seed, uint64_t counts[4], char *msg, size_t msg_len);
 
 /* ---- multi-GPU plumbing: a tile counter shared by the ranks of one node (POSIX shared memory).
  *      Replaces the per-frame static rectangles of RenderManager/TaskGenerator

@@ -208,6 +208,7 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         "ptcore_debug_trace_pixel": (C.c_int, [vp, u32, u32, i32, i32, vp, i32, C.POINTER(i32), vp]),
         "pt_bvh_selftest": (C.c_int, [C.POINTER(PtSceneDesc), i32, C.POINTER(PtStats), C.c_char_p, C.c_size_t]),
         "pt_quant_selftest": (C.c_int, [C.POINTER(PtSceneDesc), u32, u32, C.POINTER(u64), C.c_char_p, C.c_size_t]),
+        "pt_walk_selftest": (C.c_int, [C.POINTER(PtSceneDesc), u32, u32, C.POINTER(u64), C.c_char_p, C.c_size_t]),
         "pt_tileq_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
         "pt_tileq_claim": (i64, [vp, i64, i64]),
         "pt_tileq_reset": (C.c_int, [vp]),
@@ -379,6 +380,16 @@ def quant_selftest(scene: Scene, n_rays: int = 2000, seed: int = 1):
     counts = (C.c_uint64 * 3)()
     msg = C.create_string_buffer(256)
     rc = load_library().pt_quant_selftest(C.byref(d), n_rays, seed, counts, msg, 256)
+    return rc == 0, msg.value.decode(), tuple(int(c) for c in counts)
+
+
+def walk_selftest(scene: Scene, n_rays: int = 2000, seed: int = 1):
+    """(ok, message, (rays, hits, node steps on float planes, node steps on quantised planes)): host restatement of the kernel's
+    walk on both node formats against a test of every triangle (triangle-only scenes)."""
+    d, keep = scene.desc()
+    counts = (C.c_uint64 * 4)()
+    msg = C.create_string_buffer(256)
+    rc = load_library().pt_walk_selftest(C.byref(d), n_rays, seed, counts, msg, 256)
     return rc == 0, msg.value.decode(), tuple(int(c) for c in counts)
 
 

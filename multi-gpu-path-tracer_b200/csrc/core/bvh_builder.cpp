@@ -612,6 +612,165 @@ const char *check_quantised_walk(const std::vector<FlatNode> &nodes, const std::
     return "";
 }
 
+namespace {
+struct HostHit {
+    float t = FLT_MAX, u = 0.f, v = 0.f;
+    int32_t prim = -1;  // leaf-order position
+};
+// Moeller-Trumbore with the kernel's acceptance rules (strict range, reject |det| < 1e-8, barycentric bounds)
+inline bool host_triangle(const float *p, const float o[3], const float d[3], float tmin, float &t, float &u, float &v) {
+    const float e1[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]}, e2[3] = {p[6] - p[0], p[7] - p[1], p[8] - p[2]};
+    const float pv[3] = {d[1] * e2[2] - d[2] * e2[1], d[2] * e2[0] - d[0] * e2[2], d[0] * e2[1] - d[1] * e2[0]};
+    const float det = e1[0] * pv[0] + e1[1] * pv[1] + e1[2] * pv[2];
+    const float inv = 1.0f / det;
+    const float tv[3] = {o[0] - p[0], o[1] - p[1], o[2] - p[2]};
+    u = (tv[0] * pv[0] + tv[1] * pv[1] + tv[2] * pv[2]) * inv;
+    const float qv[3] = {tv[1] * e1[2] - tv[2] * e1[1], tv[2] * e1[0] - tv[0] * e1[2], tv[0] * e1[1] - tv[1] * e1[0]};
+    v = (d[0] * qv[0] + d[1] * qv[1] + d[2] * qv[2]) * inv;
+    t = (e2[0] * qv[0] + e2[1] * qv[1] + e2[2] * qv[2]) * inv;
+    const bool reject = (std::fabs(det) < 1.00000008274037e-08f) | (u < 0) | (u > 1) | (v < 0) | (u + v > 1);
+    return !reject & (t > tmin);
+}
+inline void host_accept(HostHit &best, float t, float u, float v, int32_t k) {
+    if ((t < best.t) | ((t == best.t) & (k < best.prim))) best = HostHit{t, u, v, k};
+}
+}  // namespace
+
+const char *check_walks(const BvhBuildResult &bvh, const std::vector<QuantNode> &q, const QuantGrid &g, const float *tri_pos, size_t n_tris, uint32_t n_rays,
+                        uint32_t seed, uint64_t counts[4]) {
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    if (bvh.nodes.empty() || q.size() != bvh.nodes.size() || bvh.prim_order.size() != n_tris || n_tris == 0) return "nothing to walk";
+    const int32_t kDone = (int32_t)0x80000000;
+    const float kSlack = 1.0000004f, tmin = 0.001f;
+    Lcg rng{0x51ed270b9f1a3c47ull ^ seed};
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; k++) {
+        lo[k] = g.lo[k];
+        hi[k] = g.lo[k] + 32767.0f / g.scale[k];
+    }
+    auto tri = [&](int32_t leafPos) { return tri_pos + (size_t)bvh.prim_order[(size_t)leafPos] * 9; };
+    for (uint32_t r = 0; r < n_rays; r++) {
+        float o[3], d[3];
+        const uint32_t kind = rng.next() % 4;
+        const float *aim = tri((int32_t)(rng.next() % n_tris));
+        float bu = rng.unit(), bv = rng.unit();
+        if (bu + bv > 1.f) { bu = 1.f - bu; bv = 1.f - bv; }
+        float target[3];
+        for (int k = 0; k < 3; k++) target[k] = aim[k] + bu * (aim[3 + k] - aim[k]) + bv * (aim[6 + k] - aim[k]);
+        if (kind == 0) {  // camera-like: from outside or inside the scene towards a point on a triangle
+            for (int k = 0; k < 3; k++) o[k] = lo[k] - 0.2f * (hi[k] - lo[k]) + 1.4f * (hi[k] - lo[k]) * rng.unit();
+            for (int k = 0; k < 3; k++) d[k] = target[k] - o[k];
+        } else if (kind == 1) {  // bounce-like: origin exactly on a triangle (self-intersection just above tmin is part of the game)
+            const float *from = tri((int32_t)(rng.next() % n_tris));
+            float cu = rng.unit(), cv = rng.unit();
+            if (cu + cv > 1.f) { cu = 1.f - cu; cv = 1.f - cv; }
+            for (int k = 0; k < 3; k++) o[k] = from[k] + cu * (from[3 + k] - from[k]) + cv * (from[6 + k] - from[k]);
+            for (int k = 0; k < 3; k++) d[k] = target[k] - o[k];
+        } else if (kind == 2) {  // towards a vertex or along an edge: ties between neighbouring triangles
+            for (int k = 0; k < 3; k++) o[k] = lo[k] + (hi[k] - lo[k]) * rng.unit();
+            const int corner = (int)(rng.next() % 3);
+            for (int k = 0; k < 3; k++) d[k] = aim[corner * 3 + k] - o[k];
+        } else {  // axis-parallel through a triangle point
+            const int a = (int)(rng.next() % 3);
+            for (int k = 0; k < 3; k++) { o[k] = target[k]; d[k] = 0.f; }
+            o[a] = lo[a] - 1.0f;
+            d[a] = 1.0f;
+        }
+        // 1. every triangle
+        HostHit brute;
+        for (int32_t k = 0; k < (int32_t)n_tris; k++) {
+            float t, u, v;
+            if (host_triangle(tri(k), o, d, tmin, t, u, v)) host_accept(brute, t, u, v, k);
+        }
+        // 2. / 3. the walk on float planes and on quantised planes
+        HostHit found[2];
+        for (int mode = 0; mode < 2; mode++) {
+            float inv[3], oinv[3];
+            uint32_t nearLow[3];  // quantised: does the ray reach the min plane first?
+            for (int k = 0; k < 3; k++) {
+                if (mode == 0) {
+                    inv[k] = slab_inv1(d[k]);
+                    oinv[k] = -o[k] * inv[k];
+                } else {
+                    const float og = (o[k] - g.lo[k]) * g.scale[k];
+                    inv[k] = slab_inv1(d[k] * g.scale[k]);
+                    oinv[k] = -(32768.0f + og) * inv[k];
+                }
+                nearLow[k] = !(inv[k] < 0.f);
+            }
+            HostHit best;
+            int32_t stack[64];
+            int32_t sp = 0, cur = 0, leaf = 0;
+            stack[sp++] = kDone;
+            auto held = [&]() { return (leaf & 15) != 0; };
+            uint64_t steps = 0;
+            while (!(cur == kDone && !held())) {
+                if (++steps > 100000) return "the walk does not terminate";
+                if (cur >= 0) {  // trav_node_step
+                    const FlatNode &n = bvh.nodes[(size_t)cur];
+                    const QuantNode &qn = q[(size_t)cur];
+                    float tn[2], tf[2];
+                    for (int side = 0; side < 2; side++) {
+                        tn[side] = tmin;
+                        tf[side] = best.t;
+                        const float *fb[3] = {n.bx, n.by, n.bz};
+                        const uint32_t qb[3] = {side ? qn.rx : qn.lx, side ? qn.ry : qn.ly, side ? qn.rz : qn.lz};
+                        for (int k = 0; k < 3; k++) {
+                            if (mode == 0) {
+                                const float t0 = std::fmaf(fb[k][side * 2], inv[k], oinv[k]), t1 = std::fmaf(fb[k][side * 2 + 1], inv[k], oinv[k]);
+                                tn[side] = std::fmax(tn[side], std::fmin(t0, t1));
+                                tf[side] = std::fmin(tf[side], std::fmax(t0, t1));
+                            } else {
+                                const float plo = 32768.0f + (float)(qb[k] & 0xffffu), phi = 32768.0f + (float)(qb[k] >> 16);
+                                tn[side] = std::fmax(tn[side], std::fmaf(nearLow[k] ? plo : phi, inv[k], oinv[k]));
+                                tf[side] = std::fmin(tf[side], std::fmaf(nearLow[k] ? phi : plo, inv[k], oinv[k]));
+                            }
+                        }
+                    }
+                    counts[2 + mode]++;
+                    const bool hl = tn[0] <= tf[0] * kSlack, hr = tn[1] <= tf[1] * kSlack;
+                    const bool both = hl & hr, any = hl | hr;
+                    const bool rightNear = hr & (!hl | (tn[1] < tn[0]));
+                    const int32_t nearRef = rightNear ? n.right : n.left, farRef = rightNear ? n.left : n.right;
+                    const bool holdNear = any & (nearRef < 0) & !held();
+                    const bool needPush = both & !holdNear, needPop = !any | (holdNear & !both);
+                    int32_t next = holdNear ? farRef : nearRef;
+                    if (needPush) {
+                        if (sp >= 64) return "the walk overflows the stack";
+                        stack[sp++] = farRef;
+                    }
+                    if (needPop) next = stack[--sp];
+                    if (holdNear) leaf = ~nearRef;
+                    if (next < 0 && next != kDone && !held()) {
+                        leaf = ~next;
+                        next = stack[--sp];
+                    }
+                    cur = next;
+                } else {  // trav_prim_step2
+                    const int32_t k = leaf >> 4;
+                    const bool two = (leaf & 15) >= 2;
+                    float t, u, v;
+                    if (host_triangle(tri(k), o, d, tmin, t, u, v)) host_accept(best, t, u, v, k);
+                    if (two && host_triangle(tri(k + 1), o, d, tmin, t, u, v)) host_accept(best, t, u, v, k + 1);
+                    leaf += two ? 30 : 15;
+                    if (!held() && cur < 0 && cur != kDone) {
+                        leaf = ~cur;
+                        cur = stack[--sp];
+                    }
+                }
+                if (sp < 0) return "the walk underflows the stack";
+            }
+            found[mode] = best;
+        }
+        counts[0]++;
+        counts[1] += brute.prim >= 0;
+        for (int mode = 0; mode < 2; mode++)
+            if (found[mode].prim != brute.prim || found[mode].t != brute.t || found[mode].u != brute.u || found[mode].v != brute.v)
+                return mode == 0 ? "the walk over float planes and the test of every triangle disagree" : "the walk over quantised planes and the test of every triangle disagree";
+    }
+    return "";
+}
+
 const char *validate_bvh(const BvhBuildResult &bvh, const std::vector<PrimBounds> &bounds) {
     const size_t n = bounds.size();
     if (bvh.nodes.empty()) return "no nodes";

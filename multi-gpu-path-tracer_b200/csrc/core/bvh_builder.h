@@ -106,6 +106,15 @@ const char *validate_quantised(const std::vector<FlatNode> &nodes, const std::ve
 const char *check_quantised_walk(const std::vector<FlatNode> &nodes, const std::vector<QuantNode> &q, const QuantGrid &g, uint32_t n_rays, uint32_t seed,
                                  uint32_t max_nodes, uint64_t counts[3]);
 
+// Host restatement of the kernel's resumable walk (trav_begin / trav_begin_grid, trav_node_step with the held leaf and the
+// sentinel stack, trav_prim_step2 with the tie rule) on triangle soups: for `n_rays` pseudo-random rays — camera-like,
+// bounce-like (origin on a triangle), axis-parallel — the closest hit found by the walk over float planes, by the walk over
+// quantised planes and by testing every triangle must be the same triangle at the same t.  `tri_pos` = 9 floats per
+// triangle in INPUT order (bvh.prim_order maps leaf order to it).  counts = {rays, rays that hit, node steps float, node
+// steps quantised}.  Returns "" if all three agree for every ray.
+const char *check_walks(const BvhBuildResult &bvh, const std::vector<QuantNode> &q, const QuantGrid &g, const float *tri_pos, size_t n_tris, uint32_t n_rays,
+                        uint32_t seed, uint64_t counts[4]);
+
 // Structural validation used by the tests: every primitive in exactly one leaf, child boxes
 // enclose their primitives, refs in range, depth within the device stack. Returns "" if valid.
 const char *validate_bvh(const BvhBuildResult &bvh, const std::vector<PrimBounds> &bounds);

@@ -835,6 +835,19 @@ int pt_quant_selftest(const PtSceneDesc *sc, uint32_t n_rays, uint32_t seed, uin
     return why[0] == 0 ? PT_OK : PT_ERR_SYSTEM;
 }
 
+int pt_walk_selftest(const PtSceneDesc *sc, uint32_t n_rays, uint32_t seed, uint64_t counts[4], char *msg, size_t msg_len) {
+    if (!sc || !counts || sc->n_tris <= 0 || sc->n_spheres != 0 || !sc->tri_pos) return PT_ERR_INVALID_ARGUMENT;  // triangle soups only
+    std::vector<PrimBounds> pb = padded_bounds(sc);
+    BvhBuildOptions opt;
+    BvhBuildResult bvh = build_bvh(pb, opt);
+    std::vector<QuantNode> nq;
+    QuantGrid grid = quantise_nodes(bvh.nodes, nq);
+    const char *why = validate_bvh(bvh, pb);
+    if (why[0] == 0) why = check_walks(bvh, nq, grid, sc->tri_pos, (size_t)sc->n_tris, n_rays, seed, counts);
+    if (msg && msg_len) snprintf(msg, msg_len, "%s", why);
+    return why[0] == 0 ? PT_OK : PT_ERR_SYSTEM;
+}
+
 int pt_write_ppm(const char *path, const uint8_t *rgb, uint32_t width, uint32_t height) {
     if (!path || !rgb) return PT_ERR_INVALID_ARGUMENT;
     FILE *f = fopen(path, "wb");

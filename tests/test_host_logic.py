@@ -291,3 +291,15 @@ def test_argument_loader_positionals_flags_and_errors(core_lib):
     assert exe.exists(), "run __graft_entry__.build()"
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "ARGUMENT_LOADER_TEST_OK" in r.stdout, r.stdout[-800:]
+
+
+def test_host_restatement_of_the_walk_finds_the_closest_hit_on_both_node_formats(ptb, core_lib, duck, box):
+    """pt_walk_selftest: the kernel's resumable walk (held leaf, sentinel stack, two-primitive leaf step, tie rule) restated on
+    the host, on float and on quantised planes, against a test of every triangle — camera-like, bounce-like (origin on a
+    triangle), vertex-aimed and axis-parallel rays."""
+    mesh = ptb.scenes.displaced_sphere_in_cornell(duck, n=40)
+    for scene, rays, seed in ((duck, 12000, 1), (box, 6000, 2), (mesh, 6000, 3)):
+        ok, msg, (n, hits, steps_float, steps_quant) = ptb.walk_selftest(scene, rays, seed)
+        assert ok, msg
+        assert n == rays and hits > 0.9 * rays and steps_float > 5 * rays
+        assert steps_quant < 1.05 * steps_float  # the looser boxes cost a few per cent more node steps, not more
