@@ -33,19 +33,34 @@ FLOPS_PER_RAY = lambda n_box, n_tri: 24.0 * n_box + 45.0 * n_tri + 180.0
 BYTES_PER_RAY = lambda n_box, n_tri: 32.0 * n_box + 48.0 * n_tri + 168.0
 
 
-def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE pt_wavefront_kernel launch on the default workload (1 GPU), from the
-    committed `ncu --set full` summary (profiles/r01_ncu_wavefront_final_1080p_1024spp.txt); None if absent."""
-    p = ROOT / "profiles" / "r01_ncu_wavefront_final_1080p_1024spp.txt"
+NCU_SUMMARY = {"persistent": "r02_ncu_wavefront_1080p_1024spp.txt", "pool": "r02_ncu_pool_1080p_1024spp.txt"}
+
+
+def ncu_counters(kernel: str):
+    """Per-launch counters of the dominant kernel on the default workload (1 GPU, 1080p, 1024 spp) from the committed
+    `ncu --set full` summary of the CURRENT build (profiles/r02_ncu_*_1080p_1024spp.txt, written by tools/ncu_summary.py):
+    executed warp instructions, threads per instruction, L1 / L2 / DRAM bytes.  They are properties of the (deterministic)
+    workload and the build, so dividing them by the duration measured live gives achieved rates.  None if the file is absent."""
+    p = ROOT / "profiles" / NCU_SUMMARY.get(kernel, "-")
     if not p.exists():
         return None
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    total = 0.0
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "inst": 1.0, "": 1.0, "ms": 1.0, "%": 1.0}
+    out = {}
     for ln in p.read_text().splitlines():
         f = ln.split()
-        if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[1] in scale:
-            total += float(f[2]) * scale[f[1]]
-    return total or None
+        if ln.startswith("== ") and out:
+            break  # first kernel of the file only
+        if len(f) == 3 and f[1] in scale:
+            try:
+                out[f[0]] = float(f[2]) * scale[f[1]]
+            except ValueError:
+                pass
+        elif len(f) == 2:
+            try:
+                out[f[0]] = float(f[1])
+            except ValueError:
+                pass
+    return out or None
 
 
 def measured_peaks():
@@ -191,7 +206,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="override for quick experiments (a non-default value is flagged in config)")
-    ap.add_argument("--kernel", default="persistent", choices=["persistent", "direct", "lockstep"])
+    ap.add_argument("--kernel", default="persistent", choices=["persistent", "direct", "lockstep", "pool"])
+    ap.add_argument("--smem-nodes", type=int, default=-1, help="1024-thread wavefront kernel with the quantised nodes in shared memory (-1 = library default)")
     ap.add_argument("--refill-at", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--node-burst", type=int, default=0)
@@ -245,7 +261,9 @@ def main():
     pt.upload_scene(scene)
     pt.set_camera()
     pt.set_params(spp, DEPTH)
-    pt.set_option(ptb200.PT_OPT_KERNEL, {"persistent": ptb200.PT_KERNEL_PERSISTENT, "direct": ptb200.PT_KERNEL_DIRECT, "lockstep": ptb200.PT_KERNEL_LOCKSTEP}[args.kernel])
+    pt.set_option(ptb200.PT_OPT_KERNEL, {"persistent": ptb200.PT_KERNEL_PERSISTENT, "direct": ptb200.PT_KERNEL_DIRECT, "lockstep": ptb200.PT_KERNEL_LOCKSTEP, "pool": ptb200.PT_KERNEL_POOL}[args.kernel])
+    if args.smem_nodes >= 0:
+        pt.set_option(ptb200.PT_OPT_SMEM_NODES, args.smem_nodes)
     if args.refill_at:
         pt.set_option(ptb200.PT_OPT_REFILL_AT, args.refill_at)
     if args.blocks_per_sm:
@@ -288,7 +306,7 @@ def main():
         torch.cuda.synchronize(device)
 
     def render_frame():
-        if args.sched == "lpt" and args.kernel == "persistent":
+        if args.sched == "lpt" and args.kernel in ("persistent", "pool"):
             rr.render_frame_lpt(rank, args.emulate_world or world, args.pilot_spp, gather=not args.emulate_world)
         else:
             rr.render_frame(plan, queue, rank, world)
@@ -394,21 +412,50 @@ def main():
         abytes = BYTES_PER_RAY(per_ray["box"], per_ray["tri"]) * rays_per_launch
         aflops = FLOPS_PER_RAY(per_ray["box"], per_ray["tri"]) * rays_per_launch
         sm_mhz = (clocks or {}).get("sm_mhz") or peaks["sm_max_mhz"]
-        fp32_peak_max = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-        roofline = {"bound": "hbm", "achieved": abytes / (kernel_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": abytes / (kernel_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
-                    "traffic": ncu_traffic_bytes() if (world == 1 and spp == SPP and args.kernel == "persistent") else None, "algorithmic_bytes_per_launch": abytes, "kernel": {"persistent": "pt_wavefront_kernel", "direct": "pt_direct_kernel", "lockstep": "pt_persistent_kernel"}[args.kernel],
-                    "peak_source": peaks["source"], "algorithmic_bytes_per_ray": BYTES_PER_RAY(per_ray["box"], per_ray["tri"]),
-                    "note": "algorithmic bytes (SURVEY 8d: 32 B per box test, 48 B per triangle test) are node/triangle fetches served by L1/L2 on this 1.5 MB scene; the kernel's own limiter is the ALU pipe (compare / min-max / select / permute instructions, 61 % busy at 75 % issue utilisation in profiles/r01_ncu_wavefront_final_*.txt), see DESIGN.md 4.1",
-                    "nodes": ("32-byte quantised" if (args.node_format == 2 or (args.node_format == 0 and 0 < st_build.get("quant_inflation", 0) <= 1.3)) else "64-byte float") if args.kernel == "persistent" and not args.bvh_width == 4 else "64-byte float"}
-        roofline_fp32 = {"bound": "fp32", "achieved": aflops / (kernel_ms / 1e3) / 1e12, "peak": fp32_peak_max, "unit": "TFLOP/s",
-                         "frac": aflops / (kernel_ms / 1e3) / 1e12 / fp32_peak_max, "peak_at_sustained_clock": 148 * 128 * 2 * sm_mhz * 1e6 / 1e12,
-                         "algorithmic_flops_per_ray": FLOPS_PER_RAY(per_ray["box"], per_ray["tri"])}
+        kernel_s = kernel_ms / 1e3
+        kname = {"persistent": "pt_wavefront_kernel", "pool": "pt_pool_kernel", "direct": "pt_direct_kernel", "lockstep": "pt_persistent_kernel"}[args.kernel]
+        # Three candidate roofs ("not tensor cores, not HBM for configs 2/3/5"); the one with the largest fraction binds.
+        #  (a) fp32: algorithmic FLOPs (24 per box test, 45 per triangle test, 180 per ray) against 148 SMs x 128 lanes x 2 x clock
+        #  (b) L1 / L2: bytes the kernel moves through l1tex / lts (ncu, current build) against 128 B/clk/SM and the measured
+        #      ~6300 B/clk L2 cap (B300_MICROARCH.md), at the clock sustained in this run
+        #  (c) issue: executed warp instructions (ncu, current build; the workload is deterministic) against 4 schedulers x 1
+        #      instruction per clock per SM; times threads-per-instruction / 32 = the share of lane-issue slots doing work
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        cand = {"fp32": {"bound": "fp32", "achieved": aflops / kernel_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s", "frac": aflops / kernel_s / 1e12 / fp32_peak,
+                         "algorithmic_flops_per_ray": FLOPS_PER_RAY(per_ray["box"], per_ray["tri"]), "algorithmic_flops_per_launch": aflops}}
+        nc = ncu_counters(args.kernel) if (world == 1 and spp == SPP and not args.emulate_world) else None
+        traffic = None
+        if nc:
+            traffic = nc.get("dram__bytes_read.sum", 0.0) + nc.get("dram__bytes_write.sum", 0.0)
+            issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9  # G warp-instructions / s
+            inst = nc.get("smsp__inst_executed.sum")
+            tpi = nc.get("smsp__thread_inst_executed_per_inst_executed.ratio")
+            if inst:
+                cand["issue"] = {"bound": "issue", "achieved": inst / kernel_s / 1e9, "peak": issue_peak, "unit": "G warp-instructions/s", "frac": inst / kernel_s / 1e9 / issue_peak,
+                                 "warp_instructions_per_launch": inst, "threads_per_instruction": tpi, "useful_lane_issue_frac": (inst / kernel_s / 1e9 / issue_peak) * (tpi / 32.0) if tpi else None}
+            if nc.get("l1tex__t_bytes.sum"):
+                l1_peak = 148 * 128 * sm_mhz * 1e6 / 1e9
+                cand["l1"] = {"bound": "l1", "achieved": nc["l1tex__t_bytes.sum"] / kernel_s / 1e9, "peak": l1_peak, "unit": "GB/s", "frac": nc["l1tex__t_bytes.sum"] / kernel_s / 1e9 / l1_peak}
+            if nc.get("lts__t_bytes.sum"):
+                l2_peak = 6300 * sm_mhz * 1e6 / 1e9
+                cand["l2"] = {"bound": "l2", "achieved": nc["lts__t_bytes.sum"] / kernel_s / 1e9, "peak": l2_peak, "unit": "GB/s", "frac": nc["lts__t_bytes.sum"] / kernel_s / 1e9 / l2_peak}
+            if traffic:
+                cand["hbm"] = {"bound": "hbm", "achieved": traffic / kernel_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": traffic / kernel_s / 1e9 / peaks["hbm_gbs"],
+                               "note": "real DRAM bytes of the launch (ncu), not algorithmic bytes: the 5 MB scene is cache-resident"}
+        binding = max(cand.values(), key=lambda c: c["frac"])
+        roofline = dict(binding)
+        roofline.update({"traffic": traffic, "kernel": kname, "peak_source": peaks["source"] + "; SM clock sampled during the timed region",
+                         "counters_from": ("profiles/" + NCU_SUMMARY[args.kernel]) if nc else None,
+                         "algorithmic_bytes_per_ray": BYTES_PER_RAY(per_ray["box"], per_ray["tri"]), "algorithmic_bytes_per_launch": abytes,
+                         "note": "the scene (5 MB) is L1/L2-resident, so HBM is not the roof: `bound` names the largest of the fp32 / L1 / L2 / issue / hbm fractions in `roofs`; algorithmic node+triangle bytes (SURVEY 8d) are served by L1/L2 and are reported only as algorithmic_bytes_*",
+                         "nodes": ("32-byte quantised" if (args.node_format == 2 or (args.node_format == 0 and 0 < st_build.get("quant_inflation", 0) <= 1.3)) else "64-byte float") if args.kernel in ("persistent", "pool") and not args.bvh_width == 4 else "64-byte float",
+                         "roofs": {k: {kk: vv for kk, vv in v.items() if kk in ("achieved", "peak", "unit", "frac", "useful_lane_issue_frac", "threads_per_instruction")} for k, v in cand.items()}})
+        roofline_fp32 = cand["fp32"]
         line = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "reference model cornell_duck (converted fixture), fixed XORWOW seeds",
                 "config": {"workload": WORKLOAD if spp == SPP else WORKLOAD + f" [spp overridden to {spp}]", "kernel": args.kernel, "l2": "flushed between steps (256 MiB write)",
-                           "parallelism": ("1 GPU" if world == 1 else f"{world} ranks") + (f", pilot pass ({args.pilot_spp} spp) + cost-sorted 8x4 blocks dealt round-robin (LPT), NCCL reduce gather" if args.sched == "lpt" and args.kernel == "persistent" else f", image tiles {tw}x{th}, dynamic claims of {claim}, NCCL reduce gather"),
+                           "parallelism": ("1 GPU" if world == 1 else f"{world} ranks") + (f", pilot pass ({args.pilot_spp} spp) + cost-sorted 8x4 blocks dealt round-robin (LPT), NCCL reduce gather" if args.sched == "lpt" and args.kernel in ("persistent", "pool") else f", image tiles {tw}x{th}, dynamic claims of {claim}, NCCL reduce gather"),
                            "rng": "XORWOW per pixel, reference stream order"},
                 "mrays_per_s": mrays, "rays_per_sample": rays / (samples_per_step * args.steps), "per_ray": per_ray, "wall_s_timed_region": t_wall,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_fp32": roofline_fp32}

@@ -108,7 +108,14 @@ enum { /* ptcore_set_option keys */
     PT_OPT_MIN_BLOCKS = 8,   /* accepted for compatibility: only the __launch_bounds__(128, 8) (64-register) build is shipped */
     PT_OPT_BVH_WIDTH = 9,    /* wavefront kernel: walk the 2-wide (64 B nodes, default) or the collapsed 4-wide (128 B nodes) tree; 4-wide measured 20 % slower on cornell_duck */
     PT_OPT_NODE_FORMAT = 10, /* wavefront kernel, 2-wide tree: PT_NODES_* */
-    PT_OPT_SAH_INTERSECT_COST = 11 /* next ptcore_upload_scene: cost of one primitive test relative to one node visit, in hundredths (default 120) */
+    PT_OPT_SAH_INTERSECT_COST = 11, /* next ptcore_upload_scene: cost of one primitive test relative to one node visit, in hundredths (default 120) */
+    PT_OPT_POOL_SLOTS = 12,  /* pool kernel: pixel slots per warp, 32..96 (0 = auto: pixels of the launch / warps of the grid, clamped) */
+    PT_OPT_POOL_IDLE_AT = 13,/* pool kernel: with no ready ray left, hits waiting per warp that trigger a shade pass (1..32, default 8) */
+    PT_OPT_POOL_PERIOD = 15, /* pool kernel: traverse iterations between two rounds of retiring finished rays / pulling new ones (1, 2, 4, 8; default 2) */
+    PT_OPT_POOL_CARVEOUT = 16,/* pool kernel: preferred shared-memory carve-out in percent of 228 KB (default 28 = the 64 KB configuration; -1 = driver default) */
+    PT_OPT_SMEM_NODES = 17,  /* wavefront kernel: 1 = run as one 1024-thread CTA per SM that keeps the quantised node array in shared memory (scenes whose nodes fit 160 KB) */
+    PT_OPT_LANES_PER_WARP = 18, /* wavefront kernel: lanes of every warp that take pixels (1..32, default 32) */
+    PT_OPT_WATCHDOG = 14     /* pool kernel, debugging aid: bound on the traverse iterations of a warp (0 = none); a launch that hits it renders garbage instead of hanging */
 };
 enum {
     PT_NODES_AUTO = 0,       /* default: quantised when PtStats.quant_inflation <= 1.3, else full */
@@ -118,7 +125,8 @@ enum {
 enum {
     PT_KERNEL_PERSISTENT = 0, /* persistent-thread wavefront: per-lane pixel refill + warp-voted uniform traversal steps (default) */
     PT_KERNEL_DIRECT = 1,     /* one thread per pixel, no refill: the plain parity slice */
-    PT_KERNEL_LOCKSTEP = 2    /* persistent threads with per-lane refill but a per-lane traversal loop (A/B baseline) */
+    PT_KERNEL_LOCKSTEP = 2,   /* persistent threads with per-lane refill but a per-lane traversal loop (A/B baseline) */
+    PT_KERNEL_POOL = 3        /* persistent warps with a pool of pixels each: rays are pulled by lanes from a shared-memory ring, hits are shaded one material class at a time (pt_pool.cuh) */
 };
 
 typedef struct PtStats {
@@ -134,6 +142,8 @@ typedef struct PtStats {
     uint64_t scene_bytes; /* size of the compiled device blob */
     uint32_t bvh4_nodes, bvh4_depth; /* the collapsed four-wide tree */
     double quant_inflation; /* mean over the leaves of (box area in the quantised nodes / in the float nodes); 1 = nothing lost */
+    uint32_t n_vertices;    /* unique vertex positions of the compiled scene (indexed primitive layout; 0 with the direct layout) */
+    uint32_t reserved0;
 } PtStats;
 
 /* ---- lifetime (DevicePathTracer ctor/dtor, src/DevicePathTracer.h:169-192,372-377) ---- */

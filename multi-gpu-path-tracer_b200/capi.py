@@ -22,9 +22,10 @@ LIB_PATH = PKG / "_lib" / "libptcore.so"
 
 PT_MAT_LAMBERTIAN, PT_MAT_METAL, PT_MAT_DIELECTRIC, PT_MAT_DIFFUSE_LIGHT, PT_MAT_UNIVERSAL = range(5)
 PT_OPT_KERNEL, PT_OPT_COUNT_TESTS, PT_OPT_BVH_LEAF_MAX, PT_OPT_BLOCKS_PER_SM, _PT_OPT_RESERVED_5, PT_OPT_REFILL_AT, PT_OPT_NODE_BURST, PT_OPT_MIN_BLOCKS, PT_OPT_BVH_WIDTH = range(1, 10)
-PT_KERNEL_PERSISTENT, PT_KERNEL_DIRECT, PT_KERNEL_LOCKSTEP = 0, 1, 2
+PT_KERNEL_PERSISTENT, PT_KERNEL_DIRECT, PT_KERNEL_LOCKSTEP, PT_KERNEL_POOL = 0, 1, 2, 3
 PT_OPT_NODE_FORMAT = 10
 PT_OPT_SAH_INTERSECT_COST = 11
+PT_OPT_POOL_SLOTS, PT_OPT_POOL_IDLE_AT, PT_OPT_WATCHDOG, PT_OPT_POOL_PERIOD, PT_OPT_POOL_CARVEOUT, PT_OPT_SMEM_NODES, PT_OPT_LANES_PER_WARP = 12, 13, 14, 15, 16, 17, 18
 PT_NODES_AUTO, PT_NODES_FULL, PT_NODES_QUANTISED = 0, 1, 2
 
 
@@ -60,7 +61,8 @@ class PtTile(C.Structure):
 class PtStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64), ("light_tests", C.c_uint64),
                 ("launches", C.c_uint64), ("bvh_nodes", C.c_uint32), ("bvh_leaves", C.c_uint32), ("bvh_depth", C.c_uint32), ("n_lights", C.c_uint32),
-                ("bvh_build_ms", C.c_double), ("sah_cost", C.c_double), ("scene_bytes", C.c_uint64), ("bvh4_nodes", C.c_uint32), ("bvh4_depth", C.c_uint32), ("quant_inflation", C.c_double)]
+                ("bvh_build_ms", C.c_double), ("sah_cost", C.c_double), ("scene_bytes", C.c_uint64), ("bvh4_nodes", C.c_uint32), ("bvh4_depth", C.c_uint32), ("quant_inflation", C.c_double),
+                ("n_vertices", C.c_uint32), ("reserved0", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -33,9 +33,13 @@ struct DevScene {
     const float4 *nodes;   // 4 per node     (FlatNode, bvh_builder.h)
     const uint4 *nodesq;   // 2 per node (QuantNode, bvh_builder.h): the same tree with 15-bit box planes on a scene-wide grid, 32 B per node
     const float4 *nodes4;  // 8 per wide node (FlatNode4): lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] refs[4] pad
-    const float4 *prims;   // 3 per primitive in leaf order:
-                           //   triangle: (v0.xyz, e1.x) (e1.yz, e2.xy) (e2.z, -, kind=0, -)
-                           //   sphere  : (c.xyz, r)     (-,-,-,-)      (-, -, kind=1, -)
+    const uint4 *primidx;  // PT_INDEXED_PRIMS: 1 per primitive in leaf order, (i0, i1, i2, kind | shade class << 8): indices into `verts`
+    const float4 *verts;   //   unique vertex positions (x, y, z, -), or (c.xyz, r) of a sphere
+    const float4 *prims;   // otherwise: 3 per primitive in leaf order:
+                           //   triangle: (v0.xyz, e1.x) (e1.yz, e2.xy) (e2.z, -, kind=0, shade class)
+                           //   sphere  : (c.xyz, r)     (-,-,-,-)      (-, -, kind=1, shade class)
+                           //   shade class (pool kernel): 0 = the path ends here (emitter), 1 = UniversalMaterial / lambertian bounce,
+                           //   2 = metal, 3 = dielectric
     const float4 *shade;   // 2 per primitive: (uv0, uv1) (uv2, material index, original primitive index)
     const float4 *mats;    // 3 per material : (type, base.rgb) (emis.rgb, base_tex) (emis_tex, fuzz, ior, -)
     const TexDesc *texs;
@@ -84,6 +88,14 @@ struct RenderParams {
     uint32_t pad2;
     // pilot pass (ptcore_block_costs_async): rays traced per 8x4 block are accumulated here and no pixel is stored
     uint32_t *block_cost;
+    // pool kernel (pt_pool.cuh): pixel records of this launch, 128 bytes each, pool_size per warp of the grid
+    float4 *pool_slots;
+    int32_t pool_size;     // pixel slots per warp in use (32 .. kPoolSlots)
+    int32_t pool_idle_at;  // with an empty ray ring: waiting hits per warp that trigger a shade pass
+    uint32_t watchdog;     // 0, or a bound on the traverse iterations of a warp (debugging aid: a wrong schedule must not hang the GPU)
+    int32_t pool_period;   // traverse iterations between two rounds of housekeeping (retire finished rays, pull new ones): 1, 2, 4 or 8
+    int32_t lanes_per_warp;  // wavefront kernel: lanes of a warp that take pixels (32 = all; fewer = shorter chains per pixel, see sched)
+    int32_t pad4;
     TileList tiles;
 };
 
@@ -223,6 +235,54 @@ __device__ __forceinline__ bool sphere_test(float3 center, float radius, float3 
 }
 
 // ----------------------------------------------------------------------------------------
+// primitive fetch.  Two layouts of the same data (compile-time, PT_INDEXED_PRIMS):
+//   direct    (default) 48-byte record (v0, e1, e2, kind, class), edges precomputed on the host: 3 x LDG.128, one load level.
+//   indexed   16-byte record (i0, i1, i2, kind | shade class << 8) + a table of unique vertices (float4): the hot set of
+//             cornell_duck shrinks from 203 KB to 103 KB, the 2 M-triangle mesh from 96 MB to 48 MB, at the price of one more
+//             DEPENDENT load per leaf step.  e1 = v1 - v0 and e2 = v2 - v0 are then the reference's own float subtractions
+//             (triangle.h:67-68) done per test (__fsub_rn: never contracted), so the pixels are the same.
+//             Measured on B200 (profiles/r02_prim_layout_ab.txt): -4 % on cornell_duck (2684 -> 2571 Msamples/s), -5 % on the
+//             2 M-triangle mesh (74.1 -> 77.8 ms): a warp-wide load waits for its slowest lane whatever the hit rate, so the
+//             extra load level costs more than the smaller footprint returns.  Kept as an A/B build, not shipped.
+// ----------------------------------------------------------------------------------------
+#ifndef PT_INDEXED_PRIMS
+#define PT_INDEXED_PRIMS 0
+#endif
+#ifndef PT_NODE_LDG256
+#define PT_NODE_LDG256 1
+#endif
+struct PrimGeom {
+    float3 v0, e1, e2;  // sphere: v0 = centre, e1.x = radius
+    int32_t kind;       // 0 triangle, 1 sphere
+};
+__device__ __forceinline__ PrimGeom load_prim(const DevScene &sc, int32_t k) {
+    PrimGeom g;
+#if PT_INDEXED_PRIMS
+    const uint4 r = __ldg(&sc.primidx[k]);
+    const float4 p0 = __ldg(&sc.verts[r.x]), p1 = __ldg(&sc.verts[r.y]), p2 = __ldg(&sc.verts[r.z]);
+    g.v0 = f3(p0.x, p0.y, p0.z);
+    g.kind = (int32_t)(r.w & 0xffu);
+    g.e1 = f3(__fsub_rn(p1.x, p0.x), __fsub_rn(p1.y, p0.y), __fsub_rn(p1.z, p0.z));
+    g.e2 = f3(__fsub_rn(p2.x, p0.x), __fsub_rn(p2.y, p0.y), __fsub_rn(p2.z, p0.z));
+    if (g.kind == 1) g.e1.x = p0.w;
+#else
+    const float4 q0 = __ldg(&sc.prims[k * 3 + 0]), q1 = __ldg(&sc.prims[k * 3 + 1]), q2 = __ldg(&sc.prims[k * 3 + 2]);
+    g.v0 = f3(q0.x, q0.y, q0.z);
+    g.e1 = f3(q0.w, q1.x, q1.y);
+    g.e2 = f3(q1.z, q1.w, q2.x);
+    g.kind = __float_as_int(q2.z);
+#endif
+    return g;
+}
+__device__ __forceinline__ int32_t prim_shade_class(const DevScene &sc, int32_t k) {
+#if PT_INDEXED_PRIMS
+    return (int32_t)(__ldg(&sc.primidx[k].w) >> 8);
+#else
+    return __float_as_int(__ldg(&sc.prims[k * 3 + 2]).w);
+#endif
+}
+
+// ----------------------------------------------------------------------------------------
 // closest hit: replaces BVH::hit (bvh.h:178-246) + aabb::hit (aabb.h:38-66).
 // Same result (closest accepted triangle::hit over all primitives), different walk:
 // t-culled slab tests on both children of a 64-byte node, near child first, stack of far
@@ -296,20 +356,18 @@ __device__ __forceinline__ Hit closest_hit(const DevScene &sc, float3 o, float3 
             const int32_t count = v & 15;
             for (int32_t i = 0; i < count; i++) {
                 const int32_t k = first + i;
-                const float4 q0 = __ldg(&sc.prims[k * 3 + 0]);
-                const float4 q1 = __ldg(&sc.prims[k * 3 + 1]);
-                const float4 q2 = __ldg(&sc.prims[k * 3 + 2]);
+                const PrimGeom g = load_prim(sc, k);
                 if (COUNT) n_tri += 1;
-                if (SPHERES && __float_as_int(q2.z) == 1) {
+                if (SPHERES && g.kind == 1) {
                     float t;
-                    if (sphere_test(f3(q0.x, q0.y, q0.z), q0.w, o, d, tmin, best.t, t)) {
+                    if (sphere_test(g.v0, g.e1.x, o, d, tmin, best.t, t)) {
                         best.t = t;
                         best.u = best.v = 0.f;
                         best.prim = k;
                     }
                 } else {
                     float t, u, w;
-                    if (triangle_test(f3(q0.x, q0.y, q0.z), f3(q0.w, q1.x, q1.y), f3(q1.z, q1.w, q2.x), o, d, tmin, best.t, t, u, w, k < best.prim)) {
+                    if (triangle_test(g.v0, g.e1, g.e2, o, d, tmin, best.t, t, u, w, k < best.prim)) {
                         best.t = t;
                         best.u = u;
                         best.v = w;
@@ -346,36 +404,85 @@ struct Trav {
     Hit best;
 };
 
+// Where the postponed children of a lane live.  LocalStack: a per-thread array (local memory, L1-resident).  ShortStack<K>:
+// the first K entries in shared memory — column `lane` of a [K][32] array per warp, so the 32 lanes of a warp hit 32 different
+// banks whatever their depths — and only deeper entries in a per-thread overflow array (measured with the host restatement of
+// the walk: 0.8 % of the pushes on cornell_duck and 3.5 % on a 180 K-triangle mesh go deeper than 8).
+struct LocalStack {
+    int32_t *a;
+    __device__ __forceinline__ void put(int i, int32_t v) const { a[i] = v; }
+    __device__ __forceinline__ int32_t get(int i) const { return a[i]; }
+};
+template <int K>
+struct ShortStack {
+    uint32_t col;  // shared-memory address of warp_stack[0][lane]; entry i < K is at col + i * 128
+    int32_t *ovf;  // entries K .. kStackSize-1
+    // the shared-memory access is ONE predicated instruction (no branch, so lanes at different depths do not diverge); the
+    // overflow array is touched by a few per cent of the pushes only
+    __device__ __forceinline__ void put(int i, int32_t v) const {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %0, %1;\n\t@p st.shared.b32 [%2], %3;\n\t}" ::"r"(i), "n"(K), "r"(col + (uint32_t)i * 128u), "r"(v) : "memory");
+        if (i >= K) ovf[i - K] = v;
+    }
+    __device__ __forceinline__ int32_t get(int i) const {
+        int32_t v;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %1, %2;\n\tmov.b32 %0, 0;\n\t@p ld.shared.b32 %0, [%3];\n\t}" : "=r"(v) : "r"(i), "n"(K), "r"(col + (uint32_t)i * 128u) : "memory");
+        if (i >= K) v = ovf[i - K];
+        return v;
+    }
+};
+
 __device__ __forceinline__ bool trav_leaf_held(const Trav &t) { return (t.leaf & 15) != 0; }
-__device__ __forceinline__ void trav_push(Trav &t, int32_t *stack, int32_t x) { stack[t.sp++] = x; }
-__device__ __forceinline__ int32_t trav_pop(Trav &t, int32_t *stack) { return stack[--t.sp]; }
+template <class STACK>
+__device__ __forceinline__ void trav_push(Trav &t, const STACK &stack, int32_t x) { stack.put(t.sp++, x); }
+template <class STACK>
+__device__ __forceinline__ int32_t trav_pop(Trav &t, const STACK &stack) { return stack.get(--t.sp); }
 
 __device__ __forceinline__ void trav_idle(Trav &t) {
     t.cur = kTravDone;
     t.leaf = 0;
 }
-__device__ __forceinline__ void trav_begin(Trav &t, int32_t *stack, float3 o, float3 d) {
+// A ray prepared for the slab tests: reciprocal direction and the constant term of t = plane * inv + oinv (float planes), or the
+// same in the grid coordinates of the quantised nodes (g = (x - grid_lo) * grid_scale per axis, an affine map that leaves the ray
+// parameter t unchanged; a stored plane p (15 bits) becomes the float 2^15 + p by ONE byte permute — exponent byte 0x47, p in
+// mantissa bits 8..22 — so the offset 2^15 is folded into the constant term here).
+__device__ __forceinline__ void trav_prepare(float3 o, float3 d, float3 &inv, float3 &oinv) {
+    inv = slab_inverse(d);
+    oinv = f3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+}
+__device__ __forceinline__ void trav_prepare_grid(const DevScene &sc, float3 o, float3 d, float3 &inv, float3 &oinv) {
+    const float3 og = f3((o.x - sc.grid_lo.x) * sc.grid_scale.x, (o.y - sc.grid_lo.y) * sc.grid_scale.y, (o.z - sc.grid_lo.z) * sc.grid_scale.z);
+    inv = slab_inverse(f3(d.x * sc.grid_scale.x, d.y * sc.grid_scale.y, d.z * sc.grid_scale.z));
+    oinv = f3(-(32768.0f + og.x) * inv.x, -(32768.0f + og.y) * inv.y, -(32768.0f + og.z) * inv.z);
+}
+// start the walk of a prepared ray at the root
+template <bool QUANT, class STACK>
+__device__ __forceinline__ void trav_start(Trav &t, const STACK &stack, float3 inv, float3 oinv) {
     t.cur = 0;
     t.leaf = 0;
-    stack[0] = kTravDone;
+    stack.put(0, kTravDone);
     t.sp = 1;
-    t.inv = slab_inverse(d);
-    t.oinv = f3(-o.x * t.inv.x, -o.y * t.inv.y, -o.z * t.inv.z);
+    t.inv = inv;
+    t.oinv = oinv;
     t.best.t = FLT_MAX;
     t.best.u = t.best.v = 0.f;
     t.best.prim = -1;
+    if (QUANT) {
+        // low half of a word = min plane (selector 0x7104), high half = max plane (0x7324); a ray going down an axis meets max first
+        t.sel = make_uint3(inv.x < 0.f ? 0x7324u : 0x7104u, inv.y < 0.f ? 0x7324u : 0x7104u, inv.z < 0.f ? 0x7324u : 0x7104u);
+        t.self = make_uint3(t.sel.x ^ 0x0220u, t.sel.y ^ 0x0220u, t.sel.z ^ 0x0220u);
+    }
 }
-// The same for the quantised nodes: the slab test runs in grid coordinates (g = (x - grid_lo) * grid_scale per axis, an affine
-// map that leaves the ray parameter t unchanged).  A stored plane p (15 bits) is turned into the float 2^15 + p by ONE byte
-// permute (exponent byte 0x47, p in mantissa bits 8..22), so the offset 2^15 is folded into the constant term here.
-__device__ __forceinline__ void trav_begin_grid(Trav &t, int32_t *stack, const DevScene &sc, float3 o, float3 d) {
-    trav_begin(t, stack, o, d);
-    const float3 og = f3((o.x - sc.grid_lo.x) * sc.grid_scale.x, (o.y - sc.grid_lo.y) * sc.grid_scale.y, (o.z - sc.grid_lo.z) * sc.grid_scale.z);
-    t.inv = slab_inverse(f3(d.x * sc.grid_scale.x, d.y * sc.grid_scale.y, d.z * sc.grid_scale.z));
-    t.oinv = f3(-(32768.0f + og.x) * t.inv.x, -(32768.0f + og.y) * t.inv.y, -(32768.0f + og.z) * t.inv.z);
-    // low half of a word = min plane (selector 0x7104), high half = max plane (0x7324); a ray going down an axis meets max first
-    t.sel = make_uint3(t.inv.x < 0.f ? 0x7324u : 0x7104u, t.inv.y < 0.f ? 0x7324u : 0x7104u, t.inv.z < 0.f ? 0x7324u : 0x7104u);
-    t.self = make_uint3(t.sel.x ^ 0x0220u, t.sel.y ^ 0x0220u, t.sel.z ^ 0x0220u);
+template <class STACK>
+__device__ __forceinline__ void trav_begin(Trav &t, const STACK &stack, float3 o, float3 d) {
+    float3 inv, oinv;
+    trav_prepare(o, d, inv, oinv);
+    trav_start<false>(t, stack, inv, oinv);
+}
+template <class STACK>
+__device__ __forceinline__ void trav_begin_grid(Trav &t, const STACK &stack, const DevScene &sc, float3 o, float3 d) {
+    float3 inv, oinv;
+    trav_prepare_grid(sc, o, d, inv, oinv);
+    trav_start<true>(t, stack, inv, oinv);
 }
 __device__ __forceinline__ bool trav_finished(const Trav &t) { return t.cur == kTravDone && !trav_leaf_held(t); }
 __device__ __forceinline__ void trav_hold_leaf(Trav &t, int32_t ref) { t.leaf = ~ref; }
@@ -388,15 +495,32 @@ __device__ __forceinline__ float plane_float(uint32_t word, uint32_t selector) {
 }
 
 // one inner-node step (precondition: t.cur >= 0)
-template <bool COUNT, bool QUANT = false>
-__device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, int32_t *stack, float tmin, uint32_t &n_box) {
+// SMEM: the quantised nodes were copied to shared memory by the CTA (pt_wavefront_smem_kernel); `smem_nodes` is their
+// shared-space address.  A node fetch then takes the fixed shared-memory latency instead of waiting for whichever lane of
+// the warp missed L1.
+template <bool COUNT, bool QUANT = false, class STACK = LocalStack, bool SMEM = false>
+__device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, const STACK &stack, float tmin, uint32_t &n_box, uint32_t smem_nodes = 0) {
     const float kSlack = 1.0000004f;
     const int32_t node = t.cur;
     float ln, lf, rn, rf;
     int4 refs;
     if (QUANT) {
-        const uint4 a = __ldg(&sc.nodesq[node * 2 + 0]);
-        const uint4 b = __ldg(&sc.nodesq[node * 2 + 1]);
+        // the whole 32-byte node with ONE 256-bit load (sm_100: LDG.E.256): half the load instructions of the walk
+        uint4 a, b;
+        if (SMEM) {
+            const uint32_t addr = smem_nodes + (uint32_t)node * 32u;
+            asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(addr));
+            asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(addr + 16u));
+        } else {
+#if PT_NODE_LDG256
+        asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+            : "l"(sc.nodesq + (size_t)node * 2));
+#else
+        a = __ldg(&sc.nodesq[node * 2 + 0]);
+        b = __ldg(&sc.nodesq[node * 2 + 1]);
+#endif
+        }
         if (COUNT) n_box += 2;
         // plane p -> float 2^15 + p by one byte permute; the selector picks the half of the word that the ray reaches first /
         // last on this axis (t.sel, from the sign of the direction), so no per-axis min / max is needed
@@ -445,10 +569,10 @@ __device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, int3
     const bool needPush = both & !holdNear;
     const bool needPop = !any | (holdNear & !both);
     int32_t next = holdNear ? farRef : nearRef;
-    if (needPush) stack[t.sp] = farRef;
+    if (needPush) stack.put(t.sp, farRef);
     t.sp += needPush ? 1 : 0;
     t.sp -= needPop ? 1 : 0;
-    if (needPop) next = stack[t.sp];
+    if (needPop) next = stack.get(t.sp);
     if (holdNear) trav_hold_leaf(t, nearRef);
     if (next < 0 && next != kTravDone && !trav_leaf_held(t)) {  // the successor is itself a leaf and the slot is (still) free
         trav_hold_leaf(t, next);
@@ -459,8 +583,8 @@ __device__ __forceinline__ void trav_node_step(const DevScene &sc, Trav &t, int3
 
 // one step on a four-wide node (precondition: t.cur >= 0): four independent slab tests, continue with the nearest
 // child that was hit, push the other hit children
-template <bool COUNT>
-__device__ __forceinline__ void trav_node_step4(const DevScene &sc, Trav &t, int32_t *stack, float tmin, uint32_t &n_box) {
+template <bool COUNT, class STACK = LocalStack>
+__device__ __forceinline__ void trav_node_step4(const DevScene &sc, Trav &t, const STACK &stack, float tmin, uint32_t &n_box) {
     const float kSlack = 1.0000004f;
     const float4 *nd = sc.nodes4 + (size_t)t.cur * 8;
     const float4 lox = __ldg(nd + 0), hix = __ldg(nd + 1), loy = __ldg(nd + 2), hiy = __ldg(nd + 3), loz = __ldg(nd + 4), hiz = __ldg(nd + 5);
@@ -504,23 +628,21 @@ __device__ __forceinline__ void trav_node_step4(const DevScene &sc, Trav &t, int
 }
 
 // one primitive of the held leaf (precondition: trav_leaf_held(t))
-template <bool SPHERES, bool COUNT>
-__device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, int32_t *stack, float3 o, float3 d, float tmin, uint32_t &n_tri) {
+template <bool SPHERES, bool COUNT, class STACK = LocalStack>
+__device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, const STACK &stack, float3 o, float3 d, float tmin, uint32_t &n_tri) {
     const int32_t k = t.leaf >> 4;
-    const float4 q0 = __ldg(&sc.prims[k * 3 + 0]);
-    const float4 q1 = __ldg(&sc.prims[k * 3 + 1]);
-    const float4 q2 = __ldg(&sc.prims[k * 3 + 2]);
+    const PrimGeom g = load_prim(sc, k);
     if (COUNT) n_tri += 1;
-    if (SPHERES && __float_as_int(q2.z) == 1) {
+    if (SPHERES && g.kind == 1) {
         float tt;
-        if (sphere_test(f3(q0.x, q0.y, q0.z), q0.w, o, d, tmin, t.best.t, tt)) {
+        if (sphere_test(g.v0, g.e1.x, o, d, tmin, t.best.t, tt)) {
             t.best.t = tt;
             t.best.u = t.best.v = 0.f;
             t.best.prim = k;
         }
     } else {
         float tt, u, w;
-        if (triangle_test(f3(q0.x, q0.y, q0.z), f3(q0.w, q1.x, q1.y), f3(q1.z, q1.w, q2.x), o, d, tmin, t.best.t, tt, u, w, k < t.best.prim)) {
+        if (triangle_test(g.v0, g.e1, g.e2, o, d, tmin, t.best.t, tt, u, w, k < t.best.prim)) {
             t.best.t = tt;
             t.best.u = u;
             t.best.v = w;
@@ -537,18 +659,17 @@ __device__ __forceinline__ void trav_prim_step(const DevScene &sc, Trav &t, int3
 // up to two primitives of the held leaf in one step (triangle-only scenes): the two tests are independent instruction streams
 // (a lane's chain of dependent instructions is what bounds the kernel, the FMA pipe is mostly idle), the two acceptances then
 // happen in leaf order, exactly as two single steps would
-template <bool COUNT>
-__device__ __forceinline__ void trav_prim_step2(const DevScene &sc, Trav &t, int32_t *stack, float3 o, float3 d, float tmin, uint32_t &n_tri) {
+template <bool COUNT, class STACK = LocalStack>
+__device__ __forceinline__ void trav_prim_step2(const DevScene &sc, Trav &t, const STACK &stack, float3 o, float3 d, float tmin, uint32_t &n_tri) {
     const int32_t k = t.leaf >> 4;
     const bool two = (t.leaf & 15) >= 2;
     const int32_t k1 = two ? k + 1 : k;
-    const float4 a0 = __ldg(&sc.prims[k * 3 + 0]), a1 = __ldg(&sc.prims[k * 3 + 1]), a2 = __ldg(&sc.prims[k * 3 + 2]);
-    const float4 b0 = __ldg(&sc.prims[k1 * 3 + 0]), b1 = __ldg(&sc.prims[k1 * 3 + 1]), b2 = __ldg(&sc.prims[k1 * 3 + 2]);
+    const PrimGeom ga = load_prim(sc, k), gb = load_prim(sc, k1);
     if (COUNT) n_tri += two ? 2 : 1;
     float ta, ua, va, tb, ub, vb;
     // range test against (tmin, +inf): the comparison with the current closest hit follows, in order
-    const bool oka = triangle_test(f3(a0.x, a0.y, a0.z), f3(a0.w, a1.x, a1.y), f3(a1.z, a1.w, a2.x), o, d, tmin, FLT_MAX, ta, ua, va);
-    const bool okb = triangle_test(f3(b0.x, b0.y, b0.z), f3(b0.w, b1.x, b1.y), f3(b1.z, b1.w, b2.x), o, d, tmin, FLT_MAX, tb, ub, vb) & two;
+    const bool oka = triangle_test(ga.v0, ga.e1, ga.e2, o, d, tmin, FLT_MAX, ta, ua, va);
+    const bool okb = triangle_test(gb.v0, gb.e1, gb.e2, o, d, tmin, FLT_MAX, tb, ub, vb) & two;
     if (oka & ((ta < t.best.t) | ((ta == t.best.t) & (k < t.best.prim)))) {
         t.best.t = ta;
         t.best.u = ua;
@@ -717,8 +838,8 @@ __device__ __forceinline__ bool shade(const DevScene &sc, const Hit &h, float3 &
     const float3 p = o + h.t * d;  // ray.h:19
     float3 normal;
     if (sphere) {
-        const float4 q0 = __ldg(&sc.prims[h.prim * 3 + 0]);
-        normal = (p - f3(q0.x, q0.y, q0.z)) / q0.w;  // sphere.h:33
+        const PrimGeom g = load_prim(sc, h.prim);
+        normal = (p - g.v0) / g.e1.x;  // sphere.h:33
     } else {
         normal = f3(f0.x, f0.y, f0.z);  // triangle.h:103 normalize(cross(e1, e2)) — geometric, never flipped towards the ray
     }

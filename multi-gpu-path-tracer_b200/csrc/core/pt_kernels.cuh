@@ -176,15 +176,15 @@ __global__ void __launch_bounds__(kBlockThreads) pt_persistent_kernel(const __gr
 // waiting the warp leaves TRAVERSE, shades exactly those lanes (they get their bounce ray or the next camera
 // ray) and re-enters with the unfinished lanes resuming where they stopped — warp-level ray compaction without
 // moving any state between lanes, which the one-XORWOW-stream-per-pixel contract forbids.
-template <bool SPHERES, bool RTOW, bool COUNT, int NODES>  // NODES: 0 = 64-byte two-child nodes, 1 = four-wide nodes, 2 = 32-byte quantised two-child nodes
-__global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __grid_constant__ RenderParams p) {
-    constexpr bool WIDE = NODES == 1, QUANT = NODES == 2;
+template <bool SPHERES, bool RTOW, bool COUNT, int NODES>  // NODES: 0 = 64-byte two-child nodes, 1 = four-wide nodes, 2 = 32-byte quantised two-child nodes, 3 = the same in shared memory
+__device__ __forceinline__ void wavefront_body(const RenderParams &p, const uint32_t smem_nodes) {
+    constexpr bool WIDE = NODES == 1, QUANT = NODES >= 2, SMEM = NODES == 3;
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t total_items = work_total(p);
     const int refill_at = p.refill_at;
     const int node_burst = p.node_burst;
 
-    bool retired = false, have_pixel = false, have_path = false;
+    bool retired = (int)lane >= p.lanes_per_warp, have_pixel = false, have_path = false;
     int px = 0, py = 0, pixel_index = 0;
     uint32_t samples_done = 0, bounce = 0;
     Rng rng;
@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __
     float3 col = f3(0.f, 0.f, 0.f), att = f3(1.f, 1.f, 1.f), ro = f3(0.f, 0.f, 0.f), rd = f3(0.f, 0.f, 1.f);
     uint32_t n_rays = 0, n_box = 0, n_tri = 0, n_light = 0, pixel_rays = 0;
     unsigned long long acc_box = 0, acc_tri = 0, acc_light = 0;
-    int32_t stack[kStackSize];
+    int32_t stack_mem[kStackSize];
+    const LocalStack stack{stack_mem};
     Trav tr;
     if (QUANT) trav_begin_grid(tr, stack, p.scene, ro, rd);
     else trav_begin(tr, stack, ro, rd);
@@ -259,13 +260,13 @@ __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __
             if (n_active == 0 || n_paths - n_active >= wait_for) break;
             if (__popc(m_node) >= __popc(m_prim)) {
                 if (!WIDE && node_burst == 2) {  // the default, without the loop bookkeeping
-                    if (can_node) trav_node_step<COUNT, QUANT>(p.scene, tr, stack, 0.001f, n_box);
-                    if (tr.cur >= 0) trav_node_step<COUNT, QUANT>(p.scene, tr, stack, 0.001f, n_box);
+                    if (can_node) trav_node_step<COUNT, QUANT, LocalStack, SMEM>(p.scene, tr, stack, 0.001f, n_box, smem_nodes);
+                    if (tr.cur >= 0) trav_node_step<COUNT, QUANT, LocalStack, SMEM>(p.scene, tr, stack, 0.001f, n_box, smem_nodes);
                 } else {
                     for (int k = 0; k < node_burst; k++)
                         if (tr.cur >= 0) {
                             if (WIDE) trav_node_step4<COUNT>(p.scene, tr, stack, 0.001f, n_box);
-                            else trav_node_step<COUNT, QUANT>(p.scene, tr, stack, 0.001f, n_box);
+                            else trav_node_step<COUNT, QUANT, LocalStack, SMEM>(p.scene, tr, stack, 0.001f, n_box, smem_nodes);
                         }
                 }
             } else {
@@ -316,15 +317,33 @@ __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __
     }
 }
 
+template <bool SPHERES, bool RTOW, bool COUNT, int NODES>
+__global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __grid_constant__ RenderParams p) {
+    wavefront_body<SPHERES, RTOW, COUNT, NODES>(p, 0u);
+}
+
+// The same kernel as ONE 1024-thread CTA per SM whose warps share a copy of the quantised node array in shared memory (scenes
+// whose nodes fit: cornell_duck has 2.1 K nodes = 67 KB).  The walk's node fetches — 13 of the 15 dependent loads of an average
+// ray — then cost the shared-memory latency; through L1 a warp-wide fetch waits for L2 whenever ANY of its lanes misses, which
+// at 86 % hit rate and 18 active lanes is nearly always (profiles/r01_ncu_wavefront_final_1080p_1024spp.txt: 3.0 of the 10.5
+// cycles between two issues of a warp are long-scoreboard waits).
+constexpr int kSmemKernelThreads = 1024;
+template <bool SPHERES, bool RTOW, bool COUNT>
+__global__ void __launch_bounds__(kSmemKernelThreads, 1) pt_wavefront_smem_kernel(const __grid_constant__ RenderParams p, const int32_t n_nodes) {
+    extern __shared__ uint4 smem_nodesq[];
+    for (int i = (int)threadIdx.x; i < n_nodes * 2; i += kSmemKernelThreads) smem_nodesq[i] = __ldg(&p.scene.nodesq[i]);
+    __syncthreads();
+    wavefront_body<SPHERES, RTOW, COUNT, 3>(p, (uint32_t)__cvta_generic_to_shared(smem_nodesq));
+}
+
 // Once per scene upload: the shading frame of every triangle (hit_record.normal, triangle.h:103, and the onb that
 // cosine_pdf builds from it, onb.h:8-13) and the normal of every light triangle (triangle.h:36), through the same device
 // functions a per-hit evaluation would inline, so shade() loads what the reference recomputes at every bounce.
 __global__ void pt_frames_kernel(const DevScene sc, float4 *frames, float4 *lights) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < sc.n_prims && __float_as_int(frames[k * 4 + 1].w) == 0) {
-        const float4 q0 = sc.prims[k * 3 + 0], q1 = sc.prims[k * 3 + 1], q2 = sc.prims[k * 3 + 2];
-        const float3 e1 = f3(q0.w, q1.x, q1.y), e2 = f3(q1.z, q1.w, q2.x);
-        const float3 normal = normalize(cross(e1, e2));
+        const PrimGeom g = load_prim(sc, k);
+        const float3 normal = normalize(cross(g.e1, g.e2));
         const Onb o = make_onb(normal);
         frames[k * 4 + 0] = make_float4(normal.x, normal.y, normal.z, frames[k * 4 + 0].w);
         frames[k * 4 + 1] = make_float4(o.w.x, o.w.y, o.w.z, frames[k * 4 + 1].w);
@@ -414,7 +433,8 @@ __global__ void pt_trace_kernel(const __grid_constant__ RenderParams p, int px, 
             if (MODE == 0) {
                 h = closest_hit<SPHERES, false>(p.scene, ro, rd, 0.001f, nb, nt);
             } else {
-                int32_t stack[kStackSize];
+                int32_t stack_mem[kStackSize];
+                const LocalStack stack{stack_mem};
                 Trav tr;
                 if (MODE == 2) trav_begin_grid(tr, stack, p.scene, ro, rd);
                 else trav_begin(tr, stack, ro, rd);

@@ -14,6 +14,7 @@
 
 #include "bvh_builder.h"
 #include "pt_kernels.cuh"
+#include "pt_pool.cuh"
 
 using namespace ptc;
 
@@ -29,6 +30,7 @@ struct SceneBlob {
     uint8_t *dev = nullptr;
     size_t bytes = 0;
     size_t off_nodes4 = 0;
+    size_t off_verts = 0;
     size_t off_nodes = 0, off_nodesq = 0, off_prims = 0, off_shade = 0, off_frames = 0, off_mats = 0, off_texdesc = 0, off_texels = 0, off_lights = 0;
     int32_t n_prims = 0, n_lights = 0, n_nodes = 0;
     bool has_spheres = false, has_rtow = false, has_nodes4 = false;
@@ -74,6 +76,15 @@ struct ptcore {
     int bvh_width = 2;
     int node_format = PT_NODES_AUTO;
     int sah_isect_x100 = 120;
+    int lanes_per_warp = 32;
+    int smem_nodes = 0;    // wavefront kernel: 1 = one 1024-thread CTA per SM with the quantised nodes in shared memory (when they fit)
+    int smem_nodes_max_bytes = 160 * 1024;
+    int pool_slots = 0;    // 0 = auto (pixels per warp of the launch, clamped to 32 .. kPoolSlots)
+    int pool_idle_at = 8;
+    int pool_period = 2;
+    int pool_carveout = 28;
+    uint32_t watchdog = 0;
+    bool mempool_ready = false;
     bool trace_steps = false;
     uint32_t *ident_blocks = nullptr;
     uint32_t ident_blocks_n = 0;
@@ -116,6 +127,21 @@ float triangle_area_host(const float *p) {
     return sqrtf(d) * 0.5f;
 }
 
+// Shade class of a primitive (pt_pool.cuh files finished rays under it so that one shade pass runs one branch of the integrator):
+// 0 = the path ends on this primitive (an emitter without emissive texture, material.h:62-65 / :210-217), 1 = UniversalMaterial or
+// lambertian bounce, 2 = metal, 3 = dielectric.  Scheduling only: shade() decides again from the material itself.
+int32_t shade_class(const PtMaterial &m) {
+    switch (m.type) {
+        case PT_MAT_DIFFUSE_LIGHT: return 0;
+        case PT_MAT_METAL: return 2;
+        case PT_MAT_DIELECTRIC: return 3;
+        case PT_MAT_UNIVERSAL:
+            if (m.emis_tex < 0 && (m.emis[0] * 50 > 0.0001f || m.emis[1] * 50 > 0.0001f || m.emis[2] * 50 > 0.0001f)) return 0;
+            return 1;
+        default: return 1;
+    }
+}
+
 // bounds of every primitive, padded: the slab test must never cull a hit the primitive test accepts
 std::vector<PrimBounds> padded_bounds(const PtSceneDesc *sc) {
     const int64_t n_prims = (int64_t)sc->n_tris + sc->n_spheres;
@@ -154,10 +180,68 @@ inline bool use_quantised(const ptcore *h) {
     return h->build_stats.quant_inflation > 0 && h->build_stats.quant_inflation <= 1.3;
 }
 
+// The pool kernel keeps one 128-byte record per pixel slot in global memory (pt_pool.cuh).  Launches of one handle may overlap
+// (StreamThread with several streams per GPU, tiles in flight), so every launch gets its own records from the device's
+// stream-ordered allocator; the pool keeps the memory, so after the first frames this is a pointer bump.
+template <bool S, bool R, bool C>
+cudaError_t launch_pool(ptcore *h, RenderParams rp, cudaStream_t stream) {
+    const uint32_t total = rp.tiles.first_item[rp.tiles.n];
+    void (*kernel)(RenderParams) = use_quantised(h) ? pt_pool_kernel<S, R, C, 2> : pt_pool_kernel<S, R, C, 0>;
+    // 4 CTAs x (8 warps x 1792 B + 1 KB reserved) = 60 KB: ask for the 64 KB shared-memory configuration (28 % of 228 KB) so that
+    // 192 KB stay L1; left to itself the driver picks a larger carve-out and the tree no longer fits L1
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, h->pool_carveout);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kPoolThreads, 0);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    if (h->blocks_per_sm > 0) occ = std::min(occ, std::max(1, h->blocks_per_sm * kBlockThreads / kPoolThreads));
+    uint32_t grid = (uint32_t)h->sm_count * (uint32_t)occ;
+    const uint32_t needed = (total + kPoolThreads - 1) / kPoolThreads;
+    if (grid > needed) grid = needed;
+    const uint32_t n_warps = grid * (uint32_t)kPoolWarps;
+    int pool = h->pool_slots > 0 ? h->pool_slots : (int)((total + n_warps - 1) / n_warps);
+    pool = std::max(32, std::min(pool, kPoolSlots));
+    if (!h->mempool_ready) {
+        cudaMemPool_t mp;
+        if (cudaDeviceGetDefaultMemPool(&mp, h->device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        h->mempool_ready = true;
+    }
+    void *slots = nullptr;
+    e = cudaMallocAsync(&slots, (size_t)n_warps * (size_t)pool * kPoolRecQuads * sizeof(float4), stream);
+    if (e != cudaSuccess) return e;
+    rp.pool_slots = reinterpret_cast<float4 *>(slots);
+    rp.pool_size = pool;
+    rp.pool_idle_at = h->pool_idle_at;
+    rp.pool_period = h->pool_period;
+    rp.watchdog = h->watchdog;
+    kernel<<<grid, kPoolThreads, 0, stream>>>(rp);
+    e = cudaGetLastError();
+    cudaError_t e2 = cudaFreeAsync(slots, stream);
+    return e != cudaSuccess ? e : e2;
+}
+
 template <bool S, bool R, bool C>
 cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaStream_t stream) {
     const uint32_t total = rp.tiles.first_item[rp.tiles.n];
     if (total == 0) return cudaSuccess;
+    // the pool kernel walks the two-wide tree; depth 0 (no ray at all, camera.h:52,82) stays with the wavefront kernel
+    if (h->kernel == PT_KERNEL_POOL && h->bvh_width != 4 && rp.depth > 0) return launch_pool<S, R, C>(h, rp, stream);
+    if (!direct && h->kernel == PT_KERNEL_PERSISTENT && h->smem_nodes && h->bvh_width != 4 && use_quantised(h) &&
+        (size_t)h->blob.n_nodes * 32 <= (size_t)h->smem_nodes_max_bytes) {
+        const size_t bytes = (size_t)h->blob.n_nodes * 32;
+        cudaError_t e = cudaFuncSetAttribute(pt_wavefront_smem_kernel<S, R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        uint32_t grid = (uint32_t)h->sm_count;
+        const uint32_t per_cta = (uint32_t)(kSmemKernelThreads / 32 * h->lanes_per_warp);
+        const uint32_t needed = (total + per_cta - 1) / per_cta;
+        if (grid > needed) grid = needed;
+        pt_wavefront_smem_kernel<S, R, C><<<grid, kSmemKernelThreads, bytes, stream>>>(rp, h->blob.n_nodes);
+        return cudaGetLastError();
+    }
     if (direct) {
         dim3 grid((total + kBlockThreads - 1) / kBlockThreads);
         pt_direct_kernel<S, R, C><<<grid, kBlockThreads, 0, stream>>>(rp);
@@ -171,7 +255,8 @@ cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaS
         if (occ < 1) occ = 1;
         if (h->blocks_per_sm > 0) occ = std::min(occ, h->blocks_per_sm);
         uint32_t grid = (uint32_t)h->sm_count * (uint32_t)occ;
-        uint32_t needed = (total + kBlockThreads - 1) / kBlockThreads;
+        const uint32_t per_cta = (uint32_t)(kBlockThreads / 32 * (h->kernel == PT_KERNEL_PERSISTENT ? h->lanes_per_warp : 32));
+        uint32_t needed = (total + per_cta - 1) / per_cta;
         if (grid > needed) grid = needed;
         if (h->kernel == PT_KERNEL_LOCKSTEP) pt_persistent_kernel<S, R, C><<<grid, kBlockThreads, 0, stream>>>(rp);
         else if (h->bvh_width == 4) pt_wavefront_kernel<S, R, C, 1><<<grid, kBlockThreads, 0, stream>>>(rp);
@@ -182,7 +267,7 @@ cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaS
 }
 
 cudaError_t launch(ptcore *h, const RenderParams &rp, cudaStream_t stream) {
-    if (h->kernel == PT_KERNEL_PERSISTENT && h->bvh_width == 4 && !h->blob.has_nodes4) return cudaErrorNotSupported;  // upload the scene with PT_OPT_BVH_WIDTH = 4 first
+    if ((h->kernel == PT_KERNEL_PERSISTENT || h->kernel == PT_KERNEL_POOL) && h->bvh_width == 4 && !h->blob.has_nodes4) return cudaErrorNotSupported;  // upload the scene with PT_OPT_BVH_WIDTH = 4 first
     const bool direct = h->kernel == PT_KERNEL_DIRECT;
     const bool S = h->blob.has_spheres, R = h->blob.has_rtow, C = h->count_tests;
     if (!S && !R && !C) return launch_variant<false, false, false>(h, rp, direct, stream);
@@ -205,6 +290,8 @@ void fill_dev_scene(ptcore *h) {
     d.grid_scale = make_float3(b.grid.scale[0], b.grid.scale[1], b.grid.scale[2]);
     d.pad2[0] = d.pad2[1] = 0.f;
     d.prims = reinterpret_cast<const float4 *>(b.dev + b.off_prims);
+    d.primidx = reinterpret_cast<const uint4 *>(b.dev + b.off_prims);
+    d.verts = reinterpret_cast<const float4 *>(b.dev + b.off_verts);
     d.shade = reinterpret_cast<const float4 *>(b.dev + b.off_shade);
     d.frames = reinterpret_cast<const float4 *>(b.dev + b.off_frames);
     d.mats = reinterpret_cast<const float4 *>(b.dev + b.off_mats);
@@ -222,7 +309,7 @@ int render_blocks(ptcore *h, const uint32_t *blocks_dev, uint32_t n_blocks, uint
     if (!h->have_scene) return fail(h, PT_ERR_NO_SCENE, "no scene uploaded");
     if (!h->fb_rgb) return fail(h, PT_ERR_NO_FRAMEBUFFER, "no framebuffer bound");
     if (!h->have_cam) return fail(h, PT_ERR_INVALID_ARGUMENT, "no camera set");
-    if (h->kernel != PT_KERNEL_PERSISTENT) return fail(h, PT_ERR_UNSUPPORTED, "block lists need the default (wavefront) kernel");
+    if (h->kernel != PT_KERNEL_PERSISTENT && h->kernel != PT_KERNEL_POOL) return fail(h, PT_ERR_UNSUPPORTED, "block lists need a persistent (pool or wavefront) kernel");
     if (n_blocks == 0) return PT_OK;
     if (n_blocks > 0x07ffffffu) return fail(h, PT_ERR_UNSUPPORTED, "too many blocks");
     PT_CUDA(h, cudaSetDevice(h->device));
@@ -236,6 +323,7 @@ int render_blocks(ptcore *h, const uint32_t *blocks_dev, uint32_t n_blocks, uint
     rp.depth = h->depth;
     rp.refill_at = h->refill_at;
     rp.node_burst = h->node_burst;
+    rp.lanes_per_warp = h->lanes_per_warp;
     rp.fb_rgb = h->fb_rgb;
     rp.fb_yuv = h->fb_yuv;
     rp.counters = h->d_counters;
@@ -262,6 +350,7 @@ int render_tiles(ptcore *h, const PtTile *tiles, int32_t n_tiles, cudaStream_t s
     int32_t done = 0;
     while (done < n_tiles) {
         RenderParams rp;
+        memset(&rp, 0, sizeof rp);
         rp.scene = h->dscene;
         rp.cam = h->cam;
         rp.width = h->fb_w;
@@ -270,6 +359,7 @@ int render_tiles(ptcore *h, const PtTile *tiles, int32_t n_tiles, cudaStream_t s
         rp.depth = h->depth;
         rp.refill_at = h->refill_at;
         rp.node_burst = h->node_burst;
+        rp.lanes_per_warp = h->lanes_per_warp;
         rp.fb_rgb = h->fb_rgb;
         rp.fb_yuv = h->fb_yuv;
         rp.counters = h->d_counters;
@@ -409,7 +499,56 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
     // just compete with the two-wide nodes for L2
     nb.has_nodes4 = h->bvh_width == 4 || n_prims <= (1 << 18);
     nb.off_nodes4 = off; off = align_up(off + (nb.has_nodes4 ? bvh.nodes4.size() : 1) * sizeof(FlatNode4), 256);
+#if PT_INDEXED_PRIMS
+    // unique vertices (exact bit patterns) in order of first use along the leaf order, so that neighbouring leaves share lines
+    std::vector<uint32_t> prim_index((size_t)n_prims * 4, 0u);
+    std::vector<float> verts;
+    {
+        const size_t cap_hint = (size_t)sc->n_tris * 3 + (size_t)sc->n_spheres + 1;
+        size_t cap = 16;
+        while (cap < cap_hint * 2) cap <<= 1;
+        std::vector<uint32_t> table(cap, 0xffffffffu);
+        verts.reserve(((size_t)sc->n_tris / 2 + (size_t)sc->n_spheres + 16) * 4);
+        auto intern = [&](const float *p3) -> uint32_t {
+            uint32_t b[3];
+            memcpy(b, p3, 12);
+            uint64_t hsh = (uint64_t)b[0] * 0x9E3779B97F4A7C15ull ^ ((uint64_t)b[1] * 0xC2B2AE3D27D4EB4Full + ((uint64_t)b[2] << 32 | b[2]) * 0x165667B19E3779F9ull);
+            hsh ^= hsh >> 29;
+            size_t slot = (size_t)hsh & (cap - 1);
+            for (;;) {
+                const uint32_t id = table[slot];
+                if (id == 0xffffffffu) break;
+                if (memcmp(&verts[(size_t)id * 4], p3, 12) == 0) return id;
+                slot = (slot + 1) & (cap - 1);
+            }
+            const uint32_t id = (uint32_t)(verts.size() / 4);
+            verts.insert(verts.end(), {p3[0], p3[1], p3[2], 0.f});
+            table[slot] = id;
+            return id;
+        };
+        for (int64_t k = 0; k < n_prims; k++) {
+            const int32_t id = bvh.prim_order[(size_t)k];
+            uint32_t *r = &prim_index[(size_t)k * 4];
+            if (id < sc->n_tris) {
+                const float *p = sc->tri_pos + (size_t)id * 9;
+                r[0] = intern(p); r[1] = intern(p + 3); r[2] = intern(p + 6);
+                r[3] = 0u | ((uint32_t)shade_class(sc->mats[sc->tri_mat[id]]) << 8);
+            } else {
+                const int32_t si = id - sc->n_tris;
+                const float *sp = sc->sph + (size_t)si * 4;
+                const uint32_t v = (uint32_t)(verts.size() / 4);  // spheres are not shared: (centre, radius)
+                verts.insert(verts.end(), {sp[0], sp[1], sp[2], sp[3]});
+                r[0] = r[1] = r[2] = v;
+                r[3] = 1u | ((uint32_t)shade_class(sc->mats[sc->sph_mat[si]]) << 8);
+            }
+        }
+    }
+    nb.off_prims = off; off = align_up(off + std::max<size_t>(1, (size_t)n_prims) * 16, 256);
+    nb.off_verts = off; off = align_up(off + std::max<size_t>(4, verts.size()) * sizeof(float), 256);
+#else
     nb.off_prims = off; off = align_up(off + std::max<size_t>(1, (size_t)n_prims) * 48, 256);
+    nb.off_verts = nb.off_prims;
+#endif
     nb.off_shade = off; off = align_up(off + std::max<size_t>(1, (size_t)n_prims) * 32, 256);
     nb.off_frames = off; off = align_up(off + std::max<size_t>(1, (size_t)n_prims) * 64, 256);
     nb.off_mats = off; off = align_up(off + (size_t)sc->n_mats * 48, 256);
@@ -428,12 +567,24 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
             nb.has_nodes4 = false;
         }
     }
+#if PT_INDEXED_PRIMS
+    memcpy(nb.host.data() + nb.off_prims, prim_index.data(), prim_index.size() * sizeof(uint32_t));
+    memcpy(nb.host.data() + nb.off_verts, verts.data(), verts.size() * sizeof(float));
+    h->build_stats.n_vertices = (uint32_t)(verts.size() / 4);
+#else
     float *prims = reinterpret_cast<float *>(nb.host.data() + nb.off_prims);
+    h->build_stats.n_vertices = 0;
+#endif
     float *shade = reinterpret_cast<float *>(nb.host.data() + nb.off_shade);
     float *frames = reinterpret_cast<float *>(nb.host.data() + nb.off_frames);
     for (int64_t k = 0; k < n_prims; k++) {
         int32_t id = bvh.prim_order[(size_t)k];
+#if !PT_INDEXED_PRIMS
         float *q = prims + k * 12;
+#else
+        float qdummy[12];
+        float *q = qdummy;
+#endif
         float *s = shade + k * 8;
         float *f = frames + k * 16;  // the vectors are filled in on the device (pt_frames_kernel)
         if (id < sc->n_tris) {
@@ -441,7 +592,7 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
             q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
             q[3] = p[3] - p[0]; q[4] = p[4] - p[1]; q[5] = p[5] - p[2];  // e1 = v1 - v0, triangle.h:67
             q[6] = p[6] - p[0]; q[7] = p[7] - p[1]; q[8] = p[8] - p[2];  // e2 = v2 - v0, triangle.h:68
-            q[9] = 0.f; q[10] = as_float(0); q[11] = 0.f;
+            q[9] = 0.f; q[10] = as_float(0); q[11] = as_float(shade_class(sc->mats[sc->tri_mat[id]]));
             if (sc->tri_uv) memcpy(s, sc->tri_uv + (size_t)id * 6, 6 * sizeof(float));
             s[6] = as_float(sc->tri_mat[id]);
             f[3] = s[6];
@@ -451,6 +602,7 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
             const float *sp = sc->sph + (size_t)si * 4;
             q[0] = sp[0]; q[1] = sp[1]; q[2] = sp[2]; q[3] = sp[3];
             q[10] = as_float(1);
+            q[11] = as_float(shade_class(sc->mats[sc->sph_mat[si]]));
             s[6] = as_float(sc->sph_mat[si]);
             f[3] = s[6];
             f[7] = as_float(1);
@@ -582,7 +734,7 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
     if (!h) return PT_ERR_INVALID_ARGUMENT;
     switch (key) {
         case PT_OPT_KERNEL:
-            if (value != PT_KERNEL_PERSISTENT && value != PT_KERNEL_DIRECT && value != PT_KERNEL_LOCKSTEP) return fail(h, PT_ERR_INVALID_ARGUMENT, "unknown kernel");
+            if (value != PT_KERNEL_PERSISTENT && value != PT_KERNEL_DIRECT && value != PT_KERNEL_LOCKSTEP && value != PT_KERNEL_POOL) return fail(h, PT_ERR_INVALID_ARGUMENT, "unknown kernel");
             h->kernel = (int)value;
             return PT_OK;
         case PT_OPT_COUNT_TESTS: h->count_tests = value != 0; return PT_OK;
@@ -618,6 +770,34 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
             if (value != PT_NODES_AUTO && value != PT_NODES_FULL && value != PT_NODES_QUANTISED) return fail(h, PT_ERR_INVALID_ARGUMENT, "unknown node format");
             h->node_format = (int)value;
             h->trace_steps = value != PT_NODES_AUTO;
+            return PT_OK;
+        case PT_OPT_POOL_SLOTS:
+            if (value != 0 && (value < 32 || value > kPoolSlots)) return fail(h, PT_ERR_INVALID_ARGUMENT, "pool_slots must be 0 (auto) or in [32, 96]");
+            h->pool_slots = (int)value;
+            return PT_OK;
+        case PT_OPT_POOL_IDLE_AT:
+            if (value < 1 || value > 32) return fail(h, PT_ERR_INVALID_ARGUMENT, "pool_idle_at must be in [1, 32]");
+            h->pool_idle_at = (int)value;
+            return PT_OK;
+        case PT_OPT_POOL_PERIOD:
+            if (value != 1 && value != 2 && value != 4 && value != 8) return fail(h, PT_ERR_INVALID_ARGUMENT, "pool_period must be 1, 2, 4 or 8");
+            h->pool_period = (int)value;
+            return PT_OK;
+        case PT_OPT_POOL_CARVEOUT:
+            if (value < -1 || value > 100) return fail(h, PT_ERR_INVALID_ARGUMENT, "pool_carveout is a percentage (or -1 for the driver's default)");
+            h->pool_carveout = (int)value;
+            return PT_OK;
+        case PT_OPT_SMEM_NODES:
+            if (value != 0 && value != 1) return fail(h, PT_ERR_INVALID_ARGUMENT, "smem_nodes must be 0 or 1");
+            h->smem_nodes = (int)value;
+            return PT_OK;
+        case PT_OPT_LANES_PER_WARP:
+            if (value < 1 || value > 32) return fail(h, PT_ERR_INVALID_ARGUMENT, "lanes_per_warp must be in [1, 32]");
+            h->lanes_per_warp = (int)value;
+            return PT_OK;
+        case PT_OPT_WATCHDOG:
+            if (value < 0 || value > 0xffffffffll) return fail(h, PT_ERR_INVALID_ARGUMENT, "watchdog must fit 32 bits");
+            h->watchdog = (uint32_t)value;
             return PT_OK;
         default: return fail(h, PT_ERR_UNSUPPORTED, "unknown option key");
     }

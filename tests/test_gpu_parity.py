@@ -363,3 +363,108 @@ def test_image_does_not_depend_on_the_walk_at_full_size(tracer, duck, ptb):
     tracer.set_option(ptb.PT_OPT_KERNEL, ptb.PT_KERNEL_PERSISTENT)
     assert np.array_equal(a, b) and np.array_equal(ya, yb)
     assert np.array_equal(a, c) and np.array_equal(ya, yc)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs 3, 4 and 5 at their FULL size (the oracle cannot finish a whole frame in seconds: three 4-row strips
+# of the same frame, same seeds — pixel (x, y) of a strip is pixel (x, y) of the frame).  spp is reduced, geometry is not.
+# ---------------------------------------------------------------------------------------------------------------------------
+def _strips_against_oracle(tracer, oracle, scene, w, h, spp, depth, camera, rate, rows=(0.1, 0.5, 0.85)):
+    full, _ = render(tracer, scene, w, h, spp, depth, camera)
+    st = tracer.stats()
+    assert st["samples"] == w * h * spp
+    world = oracle.world(scene)
+    out = []
+    for f in rows:
+        oy = int(h * f) // 4 * 4
+        ref, _, _ = oracle.render(world, w, h, spp, depth, camera=camera, rect=(0, oy, w, 4))
+        sl = slice(h - oy - 4, h - oy)
+        out.append(check(full[sl], ref[sl], spp, rate=rate))
+    return full, st, out
+
+
+def test_config3_sphere_field_full_size_matches_oracle_strips(tracer, oracle, ptb):
+    """BASELINE configs[2]: ~500 spheres, mixed lambertian / metal / dielectric, 1920x1080 (here at 4 of the 256 spp)."""
+    sc, cam = ptb.scenes.rtow_sphere_field()
+    full, st, m = _strips_against_oracle(tracer, oracle, sc, 1920, 1080, 4, 10, cam, rate=6e-3)
+    assert st["rays"] / st["samples"] > 1.5
+    print(m)
+
+
+def test_config4_two_million_triangles_full_size_matches_oracle_strips(tracer, oracle, duck, ptb):
+    """BASELINE configs[3]: the 2 M-triangle displaced sphere inside the cornell box at 3840x2160 (here at 2 of the 256 spp).
+    Also the structural facts that make this the memory-bound case: tree depth within the device stack, > 1 M nodes."""
+    sc = ptb.scenes.displaced_sphere_in_cornell(duck, n=1000)
+    full, st, m = _strips_against_oracle(tracer, oracle, sc, 3840, 2160, 2, 10, None, rate=3e-3)
+    assert st["bvh_depth"] <= 48 and st["bvh_nodes"] > 400_000 and st["n_lights"] == 2
+    print(m, {k: st[k] for k in ("bvh_nodes", "bvh_depth", "bvh_build_ms", "scene_bytes", "n_vertices", "quant_inflation")})
+
+
+def test_config5_cornell_duck_4k_matches_oracle_strips(tracer, oracle, duck):
+    """BASELINE configs[4] geometry: cornell_duck at 3840x2160 (here at 4 of the 4096 spp)."""
+    full, st, m = _strips_against_oracle(tracer, oracle, duck, 3840, 2160, 4, 10, None, rate=1.5e-3)
+    assert 2.3 < st["rays"] / st["samples"] < 2.7
+    print(m)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# pt_pool_kernel (pt_pool.cuh): the same pixels as the wavefront kernel and as the reference, whatever the pool does
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(REF_GPU_META) or ["<no fixtures>"])
+def test_pool_kernel_is_bit_exact_with_reference_cuda_renderer_fixtures(tracer, duck, ptb, name):
+    if not REF_GPU_META:
+        pytest.skip("tests/golden/ref_gpu_images.json not generated yet")
+    m = REF_GPU_META[name]
+    rgb, yuv = render(tracer, duck, m["width"], m["height"], m["spp"], m["depth"], _cam(m["extra"]), kernel=ptb.PT_KERNEL_POOL, ptb=ptb)
+    ref = np.array(Image.open(GOLD / f"ref_gpu_{name}.png").convert("RGB"))
+    assert np.array_equal(rgb, ref), compare(rgb, ref, m["spp"])
+    ref_yuv = np.frombuffer(gzip.decompress((GOLD / f"ref_gpu_{name}.yuv.gz").read_bytes()), np.uint8)
+    n = m["width"] * m["height"]
+    assert np.array_equal(yuv[:n], ref_yuv[:n])
+
+
+def test_pool_kernel_and_shared_memory_nodes_equal_the_wavefront_kernel(tracer, duck, ptb):
+    """Every scheduling variant renders the same bytes: pool sizes / shade thresholds / housekeeping periods of the pool kernel,
+    the 1024-thread variant of the wavefront kernel with the nodes in shared memory, fewer pixel-carrying lanes per warp;
+    triangle meshes, spheres with RTOW materials, a ragged frame, a block list."""
+    import torch
+    sc3, cam3 = ptb.scenes.mixed_material_test_scene()
+    for scene, cam, (w, h, spp, depth) in ((duck, None, (334, 186, 12, 10)), (sc3, cam3, (120, 68, 8, 8))):  # even sizes: with odd ones the I420 chroma writes alias (racy in the reference too)
+        a, ya = render(tracer, scene, w, h, spp, depth, cam, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
+        for slots, idle_at, period in ((0, 8, 2), (32, 1, 1), (96, 32, 8), (48, 4, 4)):
+            tracer.set_option(ptb.PT_OPT_POOL_SLOTS, slots)
+            tracer.set_option(ptb.PT_OPT_POOL_IDLE_AT, idle_at)
+            tracer.set_option(ptb.PT_OPT_POOL_PERIOD, period)
+            b, yb = render(tracer, scene, w, h, spp, depth, cam, kernel=ptb.PT_KERNEL_POOL, ptb=ptb)
+            assert np.array_equal(a, b) and np.array_equal(ya, yb), (slots, idle_at, period)
+        tracer.set_option(ptb.PT_OPT_POOL_SLOTS, 0)
+        tracer.set_option(ptb.PT_OPT_POOL_IDLE_AT, 8)
+        tracer.set_option(ptb.PT_OPT_POOL_PERIOD, 2)
+        tracer.set_option(ptb.PT_OPT_SMEM_NODES, 1)
+        c, yc = render(tracer, scene, w, h, spp, depth, cam, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
+        tracer.set_option(ptb.PT_OPT_LANES_PER_WARP, 5)
+        d, yd = render(tracer, scene, w, h, spp, depth, cam, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
+        tracer.set_option(ptb.PT_OPT_SMEM_NODES, 0)
+        e, ye = render(tracer, scene, w, h, spp, depth, cam, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
+        tracer.set_option(ptb.PT_OPT_LANES_PER_WARP, 32)
+        for img, y in ((c, yc), (d, yd), (e, ye)):
+            assert np.array_equal(a, img) and np.array_equal(ya, y)
+    # pool kernel on a cost-sorted block list split in two, full-size frame
+    w, h, spp, depth = 1920, 1080, 8, 10
+    full, yfull = render(tracer, duck, w, h, spp, depth, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
+    tracer.set_option(ptb.PT_OPT_KERNEL, ptb.PT_KERNEL_POOL)
+    fb = torch.zeros(h * w * 3, dtype=torch.uint8, device="cuda")
+    fy = torch.zeros(h * w * 3 // 2, dtype=torch.uint8, device="cuda")
+    tracer.bind_framebuffer(fb.data_ptr(), fy.data_ptr(), w, h)
+    bw, bh = (w + 7) // 8, (h + 3) // 4
+    costs = torch.zeros(bw * bh, dtype=torch.int32, device="cuda")
+    tracer.block_costs_async(4, costs.data_ptr())
+    order = torch.argsort(costs, descending=True, stable=True)
+    packed = ((order % bw) | ((order // bw) << 16)).to(torch.int32).contiguous()
+    halves = [packed[0::2].contiguous(), packed[1::2].contiguous()]
+    for part in halves:
+        tracer.render_blocks_async(part.data_ptr(), part.numel())
+    tracer.wait()
+    tracer.set_option(ptb.PT_OPT_KERNEL, ptb.PT_KERNEL_PERSISTENT)
+    assert np.array_equal(fb.cpu().numpy().reshape(h, w, 3), full)
+    assert np.array_equal(fy.cpu().numpy(), yfull)

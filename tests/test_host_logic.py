@@ -54,7 +54,7 @@ def test_package_never_imports_the_oracle():
 
 def test_struct_layouts_match_the_header(ptb):
     assert C.sizeof(ptb.PtMaterial) == 44 and C.sizeof(ptb.PtCamera) == 32 and C.sizeof(ptb.PtTile) == 16
-    assert C.sizeof(ptb.PtStats) == 6 * 8 + 4 * 4 + 8 + 8 + 8 + 2 * 4 + 8
+    assert C.sizeof(ptb.PtStats) == 6 * 8 + 4 * 4 + 8 + 8 + 8 + 2 * 4 + 8 + 2 * 4
 
 
 # ------------------------------------------------------------------ scene ingestion

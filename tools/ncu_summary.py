@@ -29,23 +29,40 @@ def main():
             if h in KEYS or (h.startswith('smsp__average_warps_issue_stalled') and h.endswith('per_issue_active.ratio') and float(vals[i] or 0) >= 0.15):
                 out.append(f"{h:88s} {units[i]:16s} {vals[i]}")
     src = page(rep, 'source')
-    h = src[1]
-    data = src[2:]
-    iex, ith, isrc, ismp = h.index('Instructions Executed'), h.index('Thread Instructions Executed'), h.index('Source'), h.index('# Samples')
-    tot = sum(int(r[iex]) for r in data) or 1
-    tth = sum(int(r[ith]) for r in data)
-    out.append(f"\n== SASS regions (40 instructions each): share of executed warp-instructions, threads per instruction, stall samples; overall {tth / tot:.2f} threads/instr")
-    for s in range(0, len(data), 40):
-        blk = data[s:s + 40]
-        ex = sum(int(r[iex]) for r in blk); th = sum(int(r[ith]) for r in blk); smp = sum(int(r[ismp]) for r in blk)
-        ops = {}
-        for r in blk:
-            t = r[isrc].split()
-            op = (t[1] if t and t[0].startswith('@') else (t[0] if t else '?')).split('.')[0]
-            ops[op] = ops.get(op, 0) + 1
-        top = ' '.join(f"{k}:{v}" for k, v in sorted(ops.items(), key=lambda x: -x[1])[:6])
-        if ex / tot >= 0.005:
-            out.append(f"  sass[{s:4d}..] share {100 * ex / tot:5.1f}%  thr/instr {th / max(ex, 1):5.1f}  samples {smp:7d}  {top}")
+    # one block per kernel and view ("Kernel Name" row, header row, instruction rows); the first block of a kernel is the SASS view
+    blocks, cur = [], None
+    for row in src:
+        if row and row[0] == 'Kernel Name':
+            cur = {'name': row[1], 'hdr': None, 'rows': []}
+            blocks.append(cur)
+        elif cur is not None and cur['hdr'] is None:
+            cur['hdr'] = row
+        elif cur is not None and len(row) == len(cur['hdr']):
+            cur['rows'].append(row)
+    seen = set()
+    for b in blocks:
+        if b['name'] in seen or not b['rows']:
+            continue
+        seen.add(b['name'])
+        h, data = b['hdr'], b['rows']
+        iex, ith, isrc, ismp = h.index('Instructions Executed'), h.index('Thread Instructions Executed'), h.index('Source'), h.index('# Samples')
+        stall_cols = [(i, n) for i, n in enumerate(h) if n.startswith('stall_') and not n.endswith('(Not Issued)')]
+        tot = sum(int(r[iex]) for r in data) or 1
+        tth = sum(int(r[ith]) for r in data)
+        out.append(f"\n== {b['name']}: SASS regions (40 instructions each): share of executed warp-instructions, threads per instruction, stall samples, top stalls; overall {tth / tot:.2f} threads/instr")
+        for s in range(0, len(data), 40):
+            blk = data[s:s + 40]
+            ex = sum(int(r[iex]) for r in blk); th = sum(int(r[ith]) for r in blk); smp = sum(int(r[ismp]) for r in blk)
+            ops = {}
+            for r in blk:
+                t = r[isrc].split()
+                op = (t[1] if t and t[0].startswith('@') else (t[0] if t else '?')).split('.')[0]
+                ops[op] = ops.get(op, 0) + 1
+            top = ' '.join(f"{k}:{v}" for k, v in sorted(ops.items(), key=lambda x: -x[1])[:6])
+            st = sorted(((sum(int(r[i] or 0) for r in blk), n[6:]) for i, n in stall_cols), reverse=True)[:3]
+            stx = ' '.join(f"{n}:{v}" for v, n in st if v)
+            if ex / tot >= 0.005:
+                out.append(f"  sass[{s:4d}..] share {100 * ex / tot:5.1f}%  thr/instr {th / max(ex, 1):5.1f}  samples {smp:7d}  {top} | {stx}")
     text = "\n".join(out)
     print(text)
     if len(sys.argv) > 2:
