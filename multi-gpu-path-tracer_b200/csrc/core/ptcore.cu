@@ -77,7 +77,7 @@ struct ptcore {
     int node_format = PT_NODES_AUTO;
     int sah_isect_x100 = 120;
     int lanes_per_warp = 32;
-    int smem_nodes = 0;    // wavefront kernel: 1 = one 1024-thread CTA per SM with the quantised nodes in shared memory (when they fit)
+    int smem_nodes = 1;    // wavefront kernel: 1 (default) = one 1024-thread CTA per SM with the quantised nodes in shared memory when they fit, 0 = never
     int smem_nodes_max_bytes = 160 * 1024;
     int pool_slots = 0;    // 0 = auto (pixels per warp of the launch, clamped to 32 .. kPoolSlots)
     int pool_idle_at = 8;
