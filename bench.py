@@ -156,9 +156,10 @@ def cpu_reference_sample(threads: int, rect=(640, 360, 640, 360), spp=4):
     return dict(value=n_samples / sec / 1e6, unit="Msamples/s", cores=threads, kind="port", sample=sample, seconds=sec, samples=n_samples)
 
 
-def gpu_reference_sample(spp=16):
+def gpu_reference_sample(spp=16, gpus=1):
     """The reference's own CUDA renderer (oracle/_ref/ref_gpu: RenderManager + DevicePathTracer + kernels, unmodified,
-    compiled for sm_100) on the same box: full 1920x1080 frame at reduced spp, frame >= 2 timed."""
+    compiled for sm_100) on the same box: full 1920x1080 frame at reduced spp, frame >= 2 timed; gpus > 1 = the reference's own
+    multi-GPU mode (gpuNumber = N, fixed equal tasks, one managed framebuffer, src/RenderManager.h:42-59)."""
     import tempfile
     ref_gpu = ROOT / "oracle" / "_ref" / "ref_gpu"
     if not ref_gpu.exists():
@@ -166,12 +167,12 @@ def gpu_reference_sample(spp=16):
     try:
         with tempfile.TemporaryDirectory() as td:
             flat = flat_scene_file(Path(td))
-            r = subprocess.run([str(ref_gpu), str(flat), str(WIDTH), str(HEIGHT), str(spp), str(DEPTH), "-", "--frames", "3"], capture_output=True, text=True, timeout=900)
+            r = subprocess.run([str(ref_gpu), str(flat), str(WIDTH), str(HEIGHT), str(spp), str(DEPTH), "-", "--frames", "3", "--gpus", str(gpus)], capture_output=True, text=True, timeout=900)
         line = [ln for ln in r.stdout.splitlines() if ln.startswith("REF_GPU_JSON ")]
         if r.returncode != 0 or not line:
             return {"unavailable": f"ref_gpu exited {r.returncode}: {(r.stderr or r.stdout)[-200:]}"}
         j = json.loads(line[-1][len("REF_GPU_JSON "):])
-        return dict(value=j["msamples_per_s"], unit="Msamples/s", kind="reference CUDA renderer (unmodified kernels, sm_100, 8x8 blocks)",
+        return dict(value=j["msamples_per_s"], unit="Msamples/s", n_gpus=gpus, kind="reference CUDA renderer (unmodified kernels, sm_100, 8x8 blocks" + (f", gpuNumber={gpus} FSFL)" if gpus > 1 else ")"),
                     sample=f"{WIDTH}x{HEIGHT} spp={spp} depth={DEPTH}, mean of frames 2-3", seconds=j["seconds"], init_seconds=j["init_seconds"])
     except Exception as e:  # noqa: BLE001
         return {"unavailable": f"{type(e).__name__}: {e}"}
@@ -222,6 +223,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-retire-log", action="store_true")
     ap.add_argument("--ref-sample", default="default", choices=["default", "small"], help="--impl reference: size of the bounded CPU sample (small: for tests)")
     ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
                     help="config2 (default, the bench line): 1080p/1024 spp; config5: 3840x2160/4096 spp, the strong-scaling case of BASELINE.json (a parity-test case, not the bench line)")
@@ -307,7 +309,7 @@ def main():
 
     def render_frame():
         if args.sched == "lpt" and args.kernel in ("persistent", "pool"):
-            rr.render_frame_lpt(rank, args.emulate_world or world, args.pilot_spp, gather=not args.emulate_world)
+            rr.render_frame_lpt(rank, args.emulate_world or world, args.pilot_spp, gather=not args.emulate_world, emulated=bool(args.emulate_world))
         else:
             rr.render_frame(plan, queue, rank, world)
 
@@ -344,6 +346,7 @@ def main():
         step()
     pt.reset_stats()
     rr.launches = 0
+    rr.reset_stage_times()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -355,14 +358,39 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     total_ms = float(sum(ms))
     st = pt.stats()
+    stages = rr.stage_times_ms()  # pilot / sort / render / gather, mean device ms per step on this rank
+    render_ms = stages.get("render", total_ms / args.steps)
     if world > 1:
-        t = torch.tensor([total_ms, float(st["rays"]), float(st["launches"])], dtype=torch.float64, device=device)
+        t = torch.tensor([total_ms, float(st["rays"]), float(st["launches"]), render_ms, stages.get("pilot", 0.0), stages.get("gather", 0.0)], dtype=torch.float64, device=device)
         tmax = t.clone()
+        tmin = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         total_ms, rays, launches = float(tmax[0]), float(t[1]), int(t[2])
+        stages = dict(stages, render_max_over_ranks=float(tmax[3]), render_min_over_ranks=float(tmin[3]), pilot_max_over_ranks=float(tmax[4]), gather_max_over_ranks=float(tmax[5]))
+        render_ms = float(tmax[3])
     else:
         rays, launches = float(st["rays"]), int(st["launches"])
+
+    # ---- when did the warps of the render launch retire?  One extra, untimed frame with the kernel's retire log switched on ----
+    retire = None
+    if args.sched == "lpt" and args.kernel == "persistent" and not args.no_retire_log:
+        n_log = 148 * 64
+        log = torch.zeros(2 * n_log, dtype=torch.int64, device=device)
+        pt.set_retire_log(log.data_ptr(), n_log)
+        rr.render_frame_lpt(rank, args.emulate_world or world, args.pilot_spp, gather=False, emulated=bool(args.emulate_world))
+        torch.cuda.synchronize(device)
+        pt.set_retire_log(0, 0)
+        lg = log.view(n_log, 2)
+        used = lg[:, 1] > 0
+        if bool(used.any()):
+            t0 = lg[used, 0].min()
+            ends = ((lg[used, 1] - t0).double() / 1e6).sort().values
+            q = lambda f: float(ends[min(len(ends) - 1, int(f * len(ends)))])
+            retire = {"warps": int(used.sum()), "p50_ms": q(0.50), "p90_ms": q(0.90), "p99_ms": q(0.99), "last_ms": float(ends[-1]),
+                      "note": "rank 0, one untimed frame: time from the first warp's start until 50 / 90 / 99 / 100 % of the render launch's warps had exited"}
+        barrier()
     samples_per_step = WIDTH * HEIGHT * spp
     value = samples_per_step * args.steps / (total_ms / 1e3) / 1e6
     mrays = rays / (total_ms / 1e3) / 1e6
@@ -407,7 +435,7 @@ def main():
     if rank == 0:
         peaks = measured_peaks()
         n_kernel_launches = max(1, launches)
-        kernel_ms = total_ms / args.steps                 # the dominant launch (one per rank and step) spans the step
+        kernel_ms = render_ms                             # the dominant launch (ptcore_render_blocks_async), CUDA events on its stream, mean over the timed steps (max over ranks)
         rays_per_launch = rays / (args.steps * world)      # per GPU
         abytes = BYTES_PER_RAY(per_ray["box"], per_ray["tri"]) * rays_per_launch
         aflops = FLOPS_PER_RAY(per_ray["box"], per_ray["tri"]) * rays_per_launch
@@ -458,13 +486,14 @@ def main():
                            "parallelism": ("1 GPU" if world == 1 else f"{world} ranks") + (f", pilot pass ({args.pilot_spp} spp) + cost-sorted 8x4 blocks dealt round-robin (LPT), NCCL reduce gather" if args.sched == "lpt" and args.kernel in ("persistent", "pool") else f", image tiles {tw}x{th}, dynamic claims of {claim}, NCCL reduce gather"),
                            "rng": "XORWOW per pixel, reference stream order"},
                 "mrays_per_s": mrays, "rays_per_sample": rays / (samples_per_step * args.steps), "per_ray": per_ray, "wall_s_timed_region": t_wall,
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_fp32": roofline_fp32}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_fp32": roofline_fp32,
+                "stages_ms": stages, "warp_retire": retire}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_sample(host_cores())
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        if world == 1 and not args.no_ref_gpu:
+        if not args.no_ref_gpu:
             pt.close()
-            line["ref_gpu"] = gpu_reference_sample()
+            line["ref_gpu"] = gpu_reference_sample(gpus=world)  # the reference's own CUDA renderer with gpuNumber = N (FSFL, managed framebuffer) beside our N-GPU number
         print(json.dumps(line), flush=True)
     if queue is not None:
         barrier()

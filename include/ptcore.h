@@ -115,6 +115,7 @@ enum { /* ptcore_set_option keys */
     PT_OPT_POOL_CARVEOUT = 16,/* pool kernel: preferred shared-memory carve-out in percent of 228 KB (default 28 = the 64 KB configuration; -1 = driver default) */
     PT_OPT_SMEM_NODES = 17,  /* wavefront kernel: 1 (default) = run as one 1024-thread CTA per SM that keeps the quantised node array in shared memory when it fits 160 KB (cornell_duck: 67 KB, +5 %), 0 = always fetch nodes through L1 */
     PT_OPT_LANES_PER_WARP = 18, /* wavefront kernel: lanes of every warp that take pixels (1..32, default 32) */
+    PT_OPT_STICKY_TEXTURES = 19, /* next ptcore_upload_scene: 1 (default) = a UNIVERSAL material without a texture inherits the last texture index seen, as the reference's loadMaterials does (src/DevicePathTracer.h:269-279); 0 = indices as given */
     PT_OPT_WATCHDOG = 14     /* pool kernel, debugging aid: bound on the traverse iterations of a warp (0 = none); a launch that hits it renders garbage instead of hanging */
 };
 enum {
@@ -182,6 +183,13 @@ int ptcore_render_blocks_async(ptcore_t *h, const uint32_t *blocks_dev, uint32_t
 /* Pilot pass: traces `pilot_spp` samples of every pixel (same RNG streams, nothing is stored) and accumulates the number of
  * rays per 8x4 block into costs_dev[by * ceil(W/8) + bx] (DEVICE uint32 array, zeroed by the call). */
 int ptcore_block_costs_async(ptcore_t *h, uint32_t pilot_spp, uint32_t *costs_dev, void *stream);
+/* The same for blocks [first_block, first_block + n_blocks) of the row-major block grid only (the rest of costs_dev stays zero):
+ * N ranks each measure a slice and sum the maps (one small all-reduce) instead of all tracing the whole pilot frame. */
+int ptcore_block_costs_range_async(ptcore_t *h, uint32_t pilot_spp, uint32_t *costs_dev, uint32_t first_block, uint32_t n_blocks, void *stream);
+/* Measurement aid: while set, every warp of the wavefront kernel stores the GPU's nanosecond timer at its start and at its exit into
+ * log_dev[2 * warp] / [2 * warp + 1] (DEVICE array of 2 * n_warps uint64; NULL switches it off).  bench.py derives from it when
+ * 50 / 90 / 99 % of the lanes of a launch had retired. */
+int ptcore_set_retire_log(ptcore_t *h, uint64_t *log_dev, uint32_t n_warps);
 int ptcore_sync(ptcore_t *h, void *stream);
 int ptcore_wait(ptcore_t *h);
 

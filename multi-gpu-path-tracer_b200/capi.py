@@ -25,7 +25,7 @@ PT_OPT_KERNEL, PT_OPT_COUNT_TESTS, PT_OPT_BVH_LEAF_MAX, PT_OPT_BLOCKS_PER_SM, _P
 PT_KERNEL_PERSISTENT, PT_KERNEL_DIRECT, PT_KERNEL_LOCKSTEP, PT_KERNEL_POOL = 0, 1, 2, 3
 PT_OPT_NODE_FORMAT = 10
 PT_OPT_SAH_INTERSECT_COST = 11
-PT_OPT_POOL_SLOTS, PT_OPT_POOL_IDLE_AT, PT_OPT_WATCHDOG, PT_OPT_POOL_PERIOD, PT_OPT_POOL_CARVEOUT, PT_OPT_SMEM_NODES, PT_OPT_LANES_PER_WARP = 12, 13, 14, 15, 16, 17, 18
+PT_OPT_POOL_SLOTS, PT_OPT_POOL_IDLE_AT, PT_OPT_WATCHDOG, PT_OPT_POOL_PERIOD, PT_OPT_POOL_CARVEOUT, PT_OPT_SMEM_NODES, PT_OPT_LANES_PER_WARP, PT_OPT_STICKY_TEXTURES = 12, 13, 14, 15, 16, 17, 18, 19
 PT_NODES_AUTO, PT_NODES_FULL, PT_NODES_QUANTISED = 0, 1, 2
 
 
@@ -168,7 +168,7 @@ class Scene:
         texs = []
         for i in range(d.n_tex):
             t = d.tex[i]
-            texs.append(np.ctypeslib.as_array(t.rgb, shape=(t.height, t.width, 3)).astype(np.float32).copy() if t.rgb else np.zeros((t.height, t.width, 3), np.float32))
+            texs.append(np.ctypeslib.as_array(t.rgb, shape=(t.height, t.width, 3)).astype(np.float32).copy() if t.rgb else np.zeros((0, t.width, 3), np.float32))  # no texels: height 0 = the reference's 'texture without data' (placeholder colour)
         return Scene(arr(d.tri_pos, d.n_tris * 9, np.float32).reshape(-1, 9), arr(d.tri_uv, d.n_tris * 6, np.float32).reshape(-1, 6),
                      arr(d.tri_mat, d.n_tris, np.int32), arr(d.sph, d.n_spheres * 4, np.float32).reshape(-1, 4), arr(d.sph_mat, d.n_spheres, np.int32), mats, texs)
 
@@ -202,6 +202,8 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         "ptcore_render_tiles_async": (C.c_int, [vp, C.POINTER(PtTile), i32, vp]),
         "ptcore_render_blocks_async": (C.c_int, [vp, vp, u32, vp]),
         "ptcore_block_costs_async": (C.c_int, [vp, u32, vp, vp]),
+        "ptcore_block_costs_range_async": (C.c_int, [vp, u32, vp, u32, u32, vp]),
+        "ptcore_set_retire_log": (C.c_int, [vp, vp, u32]),
         "ptcore_sync": (C.c_int, [vp, vp]),
         "ptcore_wait": (C.c_int, [vp]),
         "ptcore_render_frame_host": (C.c_int, [vp, u32, u32, vp, vp]),
@@ -344,6 +346,13 @@ class PathTracer:
     def block_costs_async(self, pilot_spp: int, costs_dev_ptr: int, stream: int = 0) -> None:
         """Pilot pass: rays per 8x4 block over pilot_spp samples into a DEVICE uint32[ceil(W/8)*ceil(H/4)] array."""
         self._ck(self.lib.ptcore_block_costs_async(self.h, pilot_spp, costs_dev_ptr, stream or None))
+
+    def block_costs_range_async(self, pilot_spp: int, costs_dev_ptr: int, first_block: int, n_blocks: int, stream: int = 0) -> None:
+        """Pilot pass over blocks [first_block, first_block + n_blocks) of the row-major block grid only."""
+        self._ck(self.lib.ptcore_block_costs_range_async(self.h, pilot_spp, costs_dev_ptr, first_block, n_blocks, stream or None))
+
+    def set_retire_log(self, log_dev_ptr: int, n_warps: int) -> None:
+        self._ck(self.lib.ptcore_set_retire_log(self.h, log_dev_ptr or None, n_warps))
 
     def sync(self, stream: int = 0) -> None:
         self._ck(self.lib.ptcore_sync(self.h, stream or None))

@@ -96,6 +96,9 @@ struct RenderParams {
     int32_t pool_period;   // traverse iterations between two rounds of housekeeping (retire finished rays, pull new ones): 1, 2, 4 or 8
     int32_t lanes_per_warp;  // wavefront kernel: lanes of a warp that take pixels (32 = all; fewer = shorter chains per pixel, see sched)
     int32_t pad4;
+    unsigned long long *retire_log;  // optional (ptcore_set_retire_log): [2 * global warp index] = globaltimer at warp start, [+1] = at warp exit
+    uint32_t retire_log_warps;       // capacity of retire_log in warps
+    uint32_t pad5;
     TileList tiles;
 };
 

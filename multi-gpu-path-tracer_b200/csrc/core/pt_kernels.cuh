@@ -22,6 +22,12 @@ namespace ptc {
 constexpr int kBlockThreads = 128;
 constexpr unsigned kFullMask = 0xffffffffu;
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // work item -> pixel.  Items enumerate 8x4 pixel blocks of each tile (32 consecutive items = one
 // block = one warp's initial fetch), so warps start on spatially coherent rays.
 __device__ __forceinline__ bool item_to_pixel(const TileList &tl, uint32_t item, int &x, int &y) {
@@ -183,6 +189,8 @@ __device__ __forceinline__ void wavefront_body(const RenderParams &p, const uint
     const uint32_t total_items = work_total(p);
     const int refill_at = p.refill_at;
     const int node_burst = p.node_burst;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p.retire_log && lane == 0 && warp_global < p.retire_log_warps) p.retire_log[2 * warp_global] = global_timer_ns();
 
     bool retired = (int)lane >= p.lanes_per_warp, have_pixel = false, have_path = false;
     int px = 0, py = 0, pixel_index = 0;
@@ -315,6 +323,7 @@ __device__ __forceinline__ void wavefront_body(const RenderParams &p, const uint
             atomicAdd(&p.counters->light_tests, acc_light);
         }
     }
+    if (p.retire_log && lane == 0 && warp_global < p.retire_log_warps) p.retire_log[2 * warp_global + 1] = global_timer_ns();
 }
 
 template <bool SPHERES, bool RTOW, bool COUNT, int NODES>

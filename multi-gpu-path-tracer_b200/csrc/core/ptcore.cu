@@ -77,6 +77,9 @@ struct ptcore {
     int node_format = PT_NODES_AUTO;
     int sah_isect_x100 = 120;
     int lanes_per_warp = 32;
+    bool sticky_textures = true;
+    unsigned long long *retire_log = nullptr;
+    uint32_t retire_log_warps = 0;
     int smem_nodes = 1;    // wavefront kernel: 1 (default) = one 1024-thread CTA per SM with the quantised nodes in shared memory when they fit, 0 = never
     int smem_nodes_max_bytes = 160 * 1024;
     int pool_slots = 0;    // 0 = auto (pixels per warp of the launch, clamped to 32 .. kPoolSlots)
@@ -87,7 +90,7 @@ struct ptcore {
     bool mempool_ready = false;
     bool trace_steps = false;
     uint32_t *ident_blocks = nullptr;
-    uint32_t ident_blocks_n = 0;
+    uint32_t ident_blocks_n = 0, ident_bw = 0;
 
     PtStats build_stats{};
 };
@@ -324,6 +327,8 @@ int render_blocks(ptcore *h, const uint32_t *blocks_dev, uint32_t n_blocks, uint
     rp.refill_at = h->refill_at;
     rp.node_burst = h->node_burst;
     rp.lanes_per_warp = h->lanes_per_warp;
+    rp.retire_log = h->retire_log;
+    rp.retire_log_warps = h->retire_log_warps;
     rp.fb_rgb = h->fb_rgb;
     rp.fb_yuv = h->fb_yuv;
     rp.counters = h->d_counters;
@@ -360,6 +365,8 @@ int render_tiles(ptcore *h, const PtTile *tiles, int32_t n_tiles, cudaStream_t s
         rp.refill_at = h->refill_at;
         rp.node_burst = h->node_burst;
         rp.lanes_per_warp = h->lanes_per_warp;
+        rp.retire_log = h->retire_log;
+        rp.retire_log_warps = h->retire_log_warps;
         rp.fb_rgb = h->fb_rgb;
         rp.fb_yuv = h->fb_yuv;
         rp.counters = h->d_counters;
@@ -611,8 +618,18 @@ int ptcore_upload_scene(ptcore_t *h, const PtSceneDesc *sc) {
         s[7] = as_float(id);
     }
     float *mats = reinterpret_cast<float *>(nb.host.data() + nb.off_mats);
+    // DevicePathTracer.h:269-279 (loadMaterials): the texture pointers live outside the loop over the materials, so a
+    // UniversalMaterial without a texture of its own inherits the last one seen.  Reproduced here, at the one place every front
+    // door (C ABI, C++ shims, Python, CLI) goes through; PT_OPT_STICKY_TEXTURES = 0 switches the quirk off.
+    int32_t sticky_base = -1, sticky_emis = -1;
     for (int32_t i = 0; i < sc->n_mats; i++) {
-        const PtMaterial &m = sc->mats[i];
+        PtMaterial m = sc->mats[i];
+        if (h->sticky_textures && m.type == PT_MAT_UNIVERSAL) {
+            if (m.base_tex >= 0) sticky_base = m.base_tex;
+            if (m.emis_tex >= 0) sticky_emis = m.emis_tex;
+            m.base_tex = sticky_base;
+            m.emis_tex = sticky_emis;
+        }
         float *q = mats + (size_t)i * 12;
         q[0] = as_float(m.type); q[1] = m.base[0]; q[2] = m.base[1]; q[3] = m.base[2];
         q[4] = m.emis[0]; q[5] = m.emis[1]; q[6] = m.emis[2]; q[7] = as_float(m.base_tex < 0 ? -1 : m.base_tex);
@@ -795,6 +812,7 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
             if (value < 1 || value > 32) return fail(h, PT_ERR_INVALID_ARGUMENT, "lanes_per_warp must be in [1, 32]");
             h->lanes_per_warp = (int)value;
             return PT_OK;
+        case PT_OPT_STICKY_TEXTURES: h->sticky_textures = value != 0; return PT_OK;
         case PT_OPT_WATCHDOG:
             if (value < 0 || value > 0xffffffffll) return fail(h, PT_ERR_INVALID_ARGUMENT, "watchdog must fit 32 bits");
             h->watchdog = (uint32_t)value;
@@ -830,13 +848,13 @@ int ptcore_render_blocks_async(ptcore_t *h, const uint32_t *blocks_dev, uint32_t
     return render_blocks(h, blocks_dev, n_blocks, h->spp, nullptr, (cudaStream_t)stream);
 }
 
-int ptcore_block_costs_async(ptcore_t *h, uint32_t pilot_spp, uint32_t *costs_dev, void *stream) {
+static int block_costs_range(ptcore_t *h, uint32_t pilot_spp, uint32_t *costs_dev, uint32_t first_block, uint32_t n_range, bool all, void *stream) {
     if (!h || !costs_dev || pilot_spp == 0) return fail(h, PT_ERR_INVALID_ARGUMENT, "bad arguments");
     if (!h->fb_rgb) return fail(h, PT_ERR_NO_FRAMEBUFFER, "no framebuffer bound");
     PT_CUDA(h, cudaSetDevice(h->device));
     const uint32_t bw = (h->fb_w + 7) / 8, bh = (h->fb_h + 3) / 4, n = bw * bh;
-    // the identity block list lives next to the cost map: costs_dev[n .. 2n)
-    if (h->ident_blocks_n != n) {
+    // identity block list of the bound framebuffer (keyed on its shape: two shapes can have the same number of blocks)
+    if (h->ident_blocks_n != n || h->ident_bw != bw) {
         std::vector<uint32_t> ident(n);
         for (uint32_t by = 0; by < bh; by++)
             for (uint32_t bx = 0; bx < bw; bx++) ident[by * bw + bx] = bx | (by << 16);
@@ -846,9 +864,31 @@ int ptcore_block_costs_async(ptcore_t *h, uint32_t pilot_spp, uint32_t *costs_de
         PT_CUDA(h, cudaMalloc(&h->ident_blocks, sizeof(uint32_t) * n));
         PT_CUDA(h, cudaMemcpy(h->ident_blocks, ident.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
         h->ident_blocks_n = n;
+        h->ident_bw = bw;
     }
+    if (all) {
+        first_block = 0;
+        n_range = n;
+    }
+    if (first_block > n) first_block = n;
+    if (n_range > n - first_block) n_range = n - first_block;
     PT_CUDA(h, cudaMemsetAsync(costs_dev, 0, sizeof(uint32_t) * n, (cudaStream_t)stream));
-    return render_blocks(h, h->ident_blocks, n, pilot_spp, costs_dev, (cudaStream_t)stream);
+    return render_blocks(h, h->ident_blocks + first_block, n_range, pilot_spp, costs_dev, (cudaStream_t)stream);
+}
+
+int ptcore_block_costs_async(ptcore_t *h, uint32_t pilot_spp, uint32_t *costs_dev, void *stream) {
+    return block_costs_range(h, pilot_spp, costs_dev, 0, 0, true, stream);
+}
+
+int ptcore_block_costs_range_async(ptcore_t *h, uint32_t pilot_spp, uint32_t *costs_dev, uint32_t first_block, uint32_t n_blocks, void *stream) {
+    return block_costs_range(h, pilot_spp, costs_dev, first_block, n_blocks, false, stream);
+}
+
+int ptcore_set_retire_log(ptcore_t *h, uint64_t *log_dev, uint32_t n_warps) {
+    if (!h) return PT_ERR_INVALID_ARGUMENT;
+    h->retire_log = reinterpret_cast<unsigned long long *>(log_dev);
+    h->retire_log_warps = log_dev ? n_warps : 0;
+    return PT_OK;
 }
 
 int ptcore_sync(ptcore_t *h, void *stream) {

@@ -17,8 +17,8 @@ struct ptscene {
 };
 
 // HostScene -> flat arrays.  Texture indices are passed through as they are: the reference's
-// "sticky" texture pointer (src/DevicePathTracer.h:269-279) is a property of its DevicePathTracer
-// and is reproduced by the C++ shim of that class, not here.
+// "sticky" texture pointer (src/DevicePathTracer.h:269-279) is applied by ptcore_upload_scene itself,
+// the one place every front door goes through.
 void ptscene_flatten(ptscene *s) {
     const HostScene &h = s->scene;
     size_t n = h.triangles.size();

@@ -342,6 +342,19 @@ HostTexture texture_from_bytes(const unsigned char *bytes, size_t n, const std::
     int w = 0, h = 0, ch = 0;
     std::vector<unsigned char> px;
     std::string err;
+    static const unsigned char png_sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    if (n < 8 || memcmp(bytes, png_sig, 8) != 0) {
+        // The reference decodes textures with stb_image (src/HostScene.cpp:10-51), which also reads JPEG / BMP / TGA / GIF / PSD / HDR; only
+        // the PNG decoder is restated here.  Such an image does not abort the load: the material keeps its slot and gets a texture
+        // without texels, which the device shades with the reference's own placeholder colour for a texture without data
+        // (242, 45, 27: src/Texture.h:33-35).  README.md / INTEGRATION.md state the restriction.
+        const char *kind = (n >= 3 && bytes[0] == 0xFF && bytes[1] == 0xD8 && bytes[2] == 0xFF) ? "JPEG" : (n >= 2 && bytes[0] == 'B' && bytes[1] == 'M') ? "BMP" : "non-PNG";
+        fprintf(stderr, "SceneLoader: texture %s is a %s image; only PNG is decoded here, the placeholder colour (242, 45, 27) is used instead\n", what.c_str(), kind);
+        HostTexture t;
+        t.width = 1;
+        t.height = 1;
+        return t;  // no data
+    }
     if (!decode_png(bytes, n, w, h, ch, px, err)) throw std::runtime_error("Cannot load texture data, path: " + what + " (" + err + ")");
     // reference src/HostScene.cpp:37-46: walks the decoded buffer 3 bytes per texel
     // whatever the channel count was; identical for 3-channel images (the duck).

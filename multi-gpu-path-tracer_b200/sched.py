@@ -47,25 +47,27 @@ class FramePlan:
 
 
 class RankRenderer:
-    """Per-rank state: tracer handle, private device framebuffer, two launch streams."""
+    """Per-rank state: tracer handle, private device framebuffer (RGB8 + I420 in ONE allocation, so the gather is one
+    collective), two launch streams, per-stage CUDA events of the last frames."""
 
     def __init__(self, pt: PathTracer, width: int, height: int, device: torch.device, n_streams: int = 2):
         self.pt = pt
         self.device = device
         self.width, self.height = width, height
-        self.rgb = torch.zeros(width * height * 3, dtype=torch.uint8, device=device)
-        self.yuv = torch.zeros(width * height * 3 // 2, dtype=torch.uint8, device=device)
+        n_rgb, n_yuv = width * height * 3, width * height * 3 // 2
+        self.fb = torch.zeros(n_rgb + n_yuv, dtype=torch.uint8, device=device)
+        self.rgb, self.yuv = self.fb[:n_rgb], self.fb[n_rgb:]
         self.streams = [torch.cuda.Stream(device=device) for _ in range(n_streams)]
         pt.bind_framebuffer(self.rgb.data_ptr(), self.yuv.data_ptr(), width, height)
         self.launches = 0
+        self.stage_events = []  # one list of (name, start event, end event) per LPT frame since the last reset_stage_times()
 
     def render_frame(self, plan: FramePlan, queue: Optional[TileQueue], rank: int, world: int, gather: bool = True) -> None:
         """Renders this rank's dynamically claimed share of the frame; after it returns, rank 0's
         self.rgb / self.yuv hold the whole frame (when gather=True and world > 1)."""
         cur = torch.cuda.current_stream(self.device)
         if world > 1:
-            self.rgb.zero_()
-            self.yuv.zero_()
+            self.fb.zero_()
         for s in self.streams:
             s.wait_stream(cur)
         n = len(plan.tiles)
@@ -89,34 +91,63 @@ class RankRenderer:
 
     def _gather(self) -> None:
         import torch.distributed as dist
-        dist.reduce(self.rgb, dst=0, op=dist.ReduceOp.SUM)
-        dist.reduce(self.yuv, dst=0, op=dist.ReduceOp.SUM)
+        dist.reduce(self.fb, dst=0, op=dist.ReduceOp.SUM)  # claimed pixel sets are disjoint, the rest is zero: a uint8 SUM is the gather
 
-    def render_frame_lpt(self, rank: int, world: int, pilot_spp: int = 4, gather: bool = True) -> None:
+    def reset_stage_times(self) -> None:
+        self.stage_events = []
+
+    def stage_times_ms(self) -> dict:
+        """Mean device milliseconds per stage (pilot, sort, render, gather) over the frames since reset_stage_times()."""
+        if not self.stage_events:
+            return {}
+        torch.cuda.synchronize(self.device)
+        acc = {}
+        for frame in self.stage_events:
+            for name, e0, e1 in frame:
+                acc.setdefault(name, []).append(e0.elapsed_time(e1))
+        return {k: sum(v) / len(v) for k, v in acc.items()}
+
+    def render_frame_lpt(self, rank: int, world: int, pilot_spp: int = 4, gather: bool = True, emulated: bool = False) -> None:
         """Cost-sorted block scheduling (longest processing time first).
 
         Every pixel is one sequential chain of spp samples (its XORWOW stream), so the unit of work cannot be split and
-        a frame ends when the last chain ends.  A pilot pass (pilot_spp samples of every pixel, a few per mille of the
-        frame) measures rays per 8x4 block; blocks are sorted by that cost, dealt round-robin to the ranks (equal cost
-        per GPU without any exchange: every rank computes the same map and the same order) and each GPU's persistent
-        kernel takes its blocks most-expensive-first, which keeps the tail of the frame short.
+        a frame ends when the last chain ends.  A pilot pass (pilot_spp samples per pixel, a few per mille of the frame)
+        measures rays per 8x4 block — each rank traces 1/world of the blocks and one all-reduce (SUM of a 260 KB map)
+        gives every rank the whole map; blocks are sorted by that cost, dealt round-robin to the ranks (equal cost per
+        GPU: every rank computes the same order) and each GPU's persistent kernel takes its blocks most-expensive-first,
+        which keeps the tail of the frame short.  `emulated`: this process stands in for rank `rank` of `world` on one
+        GPU (experiments): the pilot covers the whole frame and nothing is gathered.
         """
+        import torch.distributed as dist
         cur = torch.cuda.current_stream(self.device)
         s = self.streams[0]
         s.wait_stream(cur)
         bw, bh = (self.width + 7) // 8, (self.height + 3) // 4
-        if getattr(self, "costs", None) is None or self.costs.numel() != bw * bh:
-            self.costs = torch.zeros(bw * bh, dtype=torch.int32, device=self.device)
+        n = bw * bh
+        if getattr(self, "costs", None) is None or self.costs.numel() != n:
+            self.costs = torch.zeros(n, dtype=torch.int32, device=self.device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        distributed = world > 1 and not emulated
         with torch.cuda.stream(s):
+            ev[0].record(s)
             if world > 1:
-                self.rgb.zero_()
-                self.yuv.zero_()
-            self.pt.block_costs_async(pilot_spp, self.costs.data_ptr(), s.cuda_stream)
+                self.fb.zero_()
+            if distributed:
+                per = (n + world - 1) // world
+                self.pt.block_costs_range_async(pilot_spp, self.costs.data_ptr(), rank * per, per, s.cuda_stream)
+                dist.all_reduce(self.costs, op=dist.ReduceOp.SUM)  # NCCL enqueues on the current stream (s)
+            else:
+                self.pt.block_costs_async(pilot_spp, self.costs.data_ptr(), s.cuda_stream)
+            ev[1].record(s)
             order = torch.argsort(self.costs, descending=True, stable=True)
             mine = order[rank::world]
             self.blocks = ((mine % bw) | ((mine // bw) << 16)).to(torch.int32).contiguous()  # kept alive until the next frame
+            ev[2].record(s)
             self.pt.render_blocks_async(self.blocks.data_ptr(), int(self.blocks.numel()), s.cuda_stream)
+            ev[3].record(s)
+            if distributed and gather:
+                self._gather()
+            ev[4].record(s)
         self.launches += 2
+        self.stage_events.append([("pilot", ev[0], ev[1]), ("sort", ev[1], ev[2]), ("render", ev[2], ev[3]), ("gather", ev[3], ev[4])])
         cur.wait_stream(s)
-        if world > 1 and gather:
-            self._gather()

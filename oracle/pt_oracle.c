@@ -443,6 +443,17 @@ pto_world *pto_world_create(const PtSceneDesc *sc) {
     if (ns) { memcpy(w->sph, sc->sph, sizeof(float) * 4 * ns); memcpy(w->sph_mat, sc->sph_mat, sizeof(int32_t) * ns); }
     w->mats = (PtMaterial *)malloc(sizeof(PtMaterial) * (size_t)(sc->n_mats ? sc->n_mats : 1));
     if (sc->n_mats) memcpy(w->mats, sc->mats, sizeof(PtMaterial) * (size_t)sc->n_mats);
+    {   /* DevicePathTracer.h:269-279 (loadMaterials): the texture pointers are declared OUTSIDE the loop over the materials, so a
+         * UniversalMaterial without a texture of its own inherits the last one seen ("sticky" pointers). */
+        int sticky_base = -1, sticky_emis = -1;
+        for (int i = 0; i < sc->n_mats; i++) {
+            if (w->mats[i].type != PT_MAT_UNIVERSAL) continue;
+            if (w->mats[i].base_tex >= 0) sticky_base = w->mats[i].base_tex;
+            if (w->mats[i].emis_tex >= 0) sticky_emis = w->mats[i].emis_tex;
+            w->mats[i].base_tex = sticky_base;
+            w->mats[i].emis_tex = sticky_emis;
+        }
+    }
     w->tex = (PtTexture *)calloc((size_t)(sc->n_tex ? sc->n_tex : 1), sizeof(PtTexture));
     for (int i = 0; i < sc->n_tex; i++) {
         w->tex[i] = sc->tex[i];

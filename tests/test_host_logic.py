@@ -165,6 +165,33 @@ def test_obj_loader_routes_materials_by_name_prefix(ptb, core_lib, tmp_path):
     assert np.allclose(sc.tri_uv[0], [0, 0, 1, 0, 1, 1])
 
 
+def test_gltf_with_a_jpeg_texture_loads_with_the_placeholder_texture(ptb, core_lib, tmp_path):
+    """The reference decodes textures with stb_image (JPEG, BMP, TGA ... besides PNG, src/HostScene.cpp:10-51); only PNG is restated
+    here.  A JPEG image must not abort the load: the material keeps its texture slot and the texture has no texels,
+    which the device shades with the reference's placeholder colour for a texture without data (src/Texture.h:33-35)."""
+    import base64
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    uv = np.array([[0, 0], [1, 0], [0, 1]], np.float32)
+    blob = pos.tobytes() + uv.tobytes()
+    jpeg = bytes([0xFF, 0xD8, 0xFF, 0xE0, 0, 16]) + b"JFIF\x00" + bytes(32)
+    gltf = {
+        "asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+        "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "TEXCOORD_0": 1}, "material": 0}]}],
+        "materials": [{"name": "photo", "pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}}],
+        "textures": [{"source": 0}], "images": [{"uri": "data:image/jpeg;base64," + base64.b64encode(jpeg).decode()}],
+        "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}, {"bufferView": 1, "componentType": 5126, "count": 3, "type": "VEC2"}],
+        "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 24}],
+        "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+    }
+    path = tmp_path / "jpeg.gltf"
+    path.write_text(json.dumps(gltf))
+    sc = ptb.load_scene_file(path)
+    assert sc.tri_mat.tolist() == [0] and sc.mats["base_tex"].tolist() == [0]
+    assert len(sc.textures) == 1 and sc.textures[0].shape[0] == 0  # no texels -> placeholder colour on the device
+    again = ptb.Scene.from_ptscene_bytes(sc.to_ptscene_bytes())
+    assert again.textures[0].shape[0] == 0 and again.mats["base_tex"].tolist() == [0]
+
+
 def test_unknown_and_broken_files_raise(ptb, core_lib, tmp_path):
     (tmp_path / "a.fbx").write_text("x")
     (tmp_path / "b.glb").write_bytes(b"glTF" + b"\x00" * 30)
