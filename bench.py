@@ -224,6 +224,8 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-retire-log", action="store_true")
+    ap.add_argument("--keyed-steps", type=int, default=3, help="extra frames in the (pixel, sample)-keyed RNG mode, reported under `rng_keyed` (0 = skip)")
+    ap.add_argument("--keyed-chunks", type=int, default=32)
     ap.add_argument("--ref-sample", default="default", choices=["default", "small"], help="--impl reference: size of the bounded CPU sample (small: for tests)")
     ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
                     help="config2 (default, the bench line): 1080p/1024 spp; config5: 3840x2160/4096 spp, the strong-scaling case of BASELINE.json (a parity-test case, not the bench line)")
@@ -395,6 +397,32 @@ def main():
     value = samples_per_step * args.steps / (total_ms / 1e3) / 1e6
     mrays = rays / (total_ms / 1e3) / 1e6
 
+    # ---- the same frame in the (pixel, sample)-keyed RNG mode (statistical parity only: reported separately, never the bench value) ----
+    keyed = None
+    if args.keyed_steps > 0 and args.kernel == "persistent" and args.sched == "lpt":
+        def keyed_step():
+            flush.zero_()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rr.render_frame_keyed(rank, args.emulate_world or world, args.keyed_chunks, args.pilot_spp, gather=not args.emulate_world, emulated=bool(args.emulate_world))
+            e1.record()
+            e1.synchronize()
+            return e0.elapsed_time(e1)
+        keyed_step()
+        rr.reset_stage_times()
+        kms = float(sum(keyed_step() for _ in range(args.keyed_steps)))
+        kstages = rr.stage_times_ms()
+        if world > 1:
+            kt = torch.tensor([kms], dtype=torch.float64, device=device)
+            dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+            kms = float(kt[0])
+        keyed = {"value": WIDTH * HEIGHT * spp * args.keyed_steps / (kms / 1e3) / 1e6, "unit": "Msamples/s", "ms_per_step": kms / args.keyed_steps, "steps": args.keyed_steps,
+                 "chunks_per_pixel": args.keyed_chunks, "stages_ms": kstages,
+                 "rng": "XORWOW keyed by (pixel, sample): curand_init(1984 + pixel + sample * W * H, 0, 0); parity with the reference is statistical in this mode (converged RMSE <= 1/255, tests/test_gpu_parity.py)",
+                 "parallelism": "rank r traces chunks r, r + N, ... of every pixel; one float reduce of the chunk sums; rank 0 adds them in chunk order"}
+        rr.reset_stage_times()
+
     # ---- end to end through the C ABI with host buffers ----
     e2e = None
     if not args.no_e2e:
@@ -487,7 +515,7 @@ def main():
                            "rng": "XORWOW per pixel, reference stream order"},
                 "mrays_per_s": mrays, "rays_per_sample": rays / (samples_per_step * args.steps), "per_ray": per_ray, "wall_s_timed_region": t_wall,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_fp32": roofline_fp32,
-                "stages_ms": stages, "warp_retire": retire}
+                "stages_ms": stages, "warp_retire": retire, "rng_keyed": keyed}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_sample(host_cores())
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

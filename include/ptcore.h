@@ -116,7 +116,18 @@ enum { /* ptcore_set_option keys */
     PT_OPT_SMEM_NODES = 17,  /* wavefront kernel: 1 (default) = run as one 1024-thread CTA per SM that keeps the quantised node array in shared memory when it fits 160 KB (cornell_duck: 67 KB, +5 %), 0 = always fetch nodes through L1 */
     PT_OPT_LANES_PER_WARP = 18, /* wavefront kernel: lanes of every warp that take pixels (1..32, default 32) */
     PT_OPT_STICKY_TEXTURES = 19, /* next ptcore_upload_scene: 1 (default) = a UNIVERSAL material without a texture inherits the last texture index seen, as the reference's loadMaterials does (src/DevicePathTracer.h:269-279); 0 = indices as given */
+    PT_OPT_RNG_MODE = 20,    /* PT_RNG_*: which random stream ptcore_render_frame_host uses (the explicit ptcore_render_keyed_async is always keyed) */
+    PT_OPT_RNG_CHUNKS = 21,  /* PT_RNG_SAMPLE_KEYED through ptcore_render_frame_host: work items per pixel (default 16) */
     PT_OPT_WATCHDOG = 14     /* pool kernel, debugging aid: bound on the traverse iterations of a warp (0 = none); a launch that hits it renders garbage instead of hanging */
+};
+enum {
+    PT_RNG_STREAM = 0,       /* default, the parity mode: one XORWOW stream per pixel, curand_init(1984 + pixel, 0, 0), samples consumed in
+                                sequence exactly as the reference does (src/DevicePathTracer.h:54,80-87): bit-exact images, but a pixel's
+                                spp samples form ONE sequential chain */
+    PT_RNG_SAMPLE_KEYED = 1  /* throughput mode: the stream is keyed by (pixel, sample): sample s of pixel p draws from
+                                curand_init(1984 + p + s * W * H, 0, 0); a pixel's samples are independent work items.  Same estimator,
+                                different random numbers: parity is statistical (converged RMSE), images are still independent of how the
+                                work is split over launches and GPUs */
 };
 enum {
     PT_NODES_AUTO = 0,       /* default: quantised when PtStats.quant_inflation <= 1.3, else full */
@@ -186,6 +197,14 @@ int ptcore_block_costs_async(ptcore_t *h, uint32_t pilot_spp, uint32_t *costs_de
 /* The same for blocks [first_block, first_block + n_blocks) of the row-major block grid only (the rest of costs_dev stays zero):
  * N ranks each measure a slice and sum the maps (one small all-reduce) instead of all tracing the whole pilot frame. */
 int ptcore_block_costs_range_async(ptcore_t *h, uint32_t pilot_spp, uint32_t *costs_dev, uint32_t first_block, uint32_t n_blocks, void *stream);
+/* PT_RNG_SAMPLE_KEYED, explicit form.  A pixel's spp samples are cut into n_chunks chunks of ceil(spp / n_chunks); this call traces chunks
+ * first_chunk, first_chunk + chunk_step, ... of every pixel of the listed 8x4 blocks (blocks_dev == NULL: the whole bound framebuffer) and
+ * stores each chunk's colour sum to accum_dev[(chunk * W * H + pixel) * 3 .. + 3) (DEVICE floats, zeroed by the caller).  N ranks take
+ * first_chunk = rank, chunk_step = N and sum their buffers (each entry is written by exactly one rank, so the float sum is exact).
+ * ptcore_resolve_keyed_async then adds the chunks of every pixel in chunk order and stores RGB8 + I420 into the bound framebuffer. */
+int ptcore_render_keyed_async(ptcore_t *h, const uint32_t *blocks_dev, uint32_t n_blocks, float *accum_dev, uint32_t n_chunks, uint32_t first_chunk, uint32_t chunk_step,
+                              void *stream);
+int ptcore_resolve_keyed_async(ptcore_t *h, const float *accum_dev, uint32_t n_chunks, void *stream);
 /* Measurement aid: while set, every warp of the wavefront kernel stores the GPU's nanosecond timer at its start and at its exit into
  * log_dev[2 * warp] / [2 * warp + 1] (DEVICE array of 2 * n_warps uint64; NULL switches it off).  bench.py derives from it when
  * 50 / 90 / 99 % of the lanes of a launch had retired. */

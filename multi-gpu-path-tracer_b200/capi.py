@@ -25,7 +25,8 @@ PT_OPT_KERNEL, PT_OPT_COUNT_TESTS, PT_OPT_BVH_LEAF_MAX, PT_OPT_BLOCKS_PER_SM, _P
 PT_KERNEL_PERSISTENT, PT_KERNEL_DIRECT, PT_KERNEL_LOCKSTEP, PT_KERNEL_POOL = 0, 1, 2, 3
 PT_OPT_NODE_FORMAT = 10
 PT_OPT_SAH_INTERSECT_COST = 11
-PT_OPT_POOL_SLOTS, PT_OPT_POOL_IDLE_AT, PT_OPT_WATCHDOG, PT_OPT_POOL_PERIOD, PT_OPT_POOL_CARVEOUT, PT_OPT_SMEM_NODES, PT_OPT_LANES_PER_WARP, PT_OPT_STICKY_TEXTURES = 12, 13, 14, 15, 16, 17, 18, 19
+PT_OPT_POOL_SLOTS, PT_OPT_POOL_IDLE_AT, PT_OPT_WATCHDOG, PT_OPT_POOL_PERIOD, PT_OPT_POOL_CARVEOUT, PT_OPT_SMEM_NODES, PT_OPT_LANES_PER_WARP, PT_OPT_STICKY_TEXTURES, PT_OPT_RNG_MODE, PT_OPT_RNG_CHUNKS = 12, 13, 14, 15, 16, 17, 18, 19, 20, 21
+PT_RNG_STREAM, PT_RNG_SAMPLE_KEYED = 0, 1
 PT_NODES_AUTO, PT_NODES_FULL, PT_NODES_QUANTISED = 0, 1, 2
 
 
@@ -204,6 +205,8 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         "ptcore_block_costs_async": (C.c_int, [vp, u32, vp, vp]),
         "ptcore_block_costs_range_async": (C.c_int, [vp, u32, vp, u32, u32, vp]),
         "ptcore_set_retire_log": (C.c_int, [vp, vp, u32]),
+        "ptcore_render_keyed_async": (C.c_int, [vp, vp, u32, vp, u32, u32, u32, vp]),
+        "ptcore_resolve_keyed_async": (C.c_int, [vp, vp, u32, vp]),
         "ptcore_sync": (C.c_int, [vp, vp]),
         "ptcore_wait": (C.c_int, [vp]),
         "ptcore_render_frame_host": (C.c_int, [vp, u32, u32, vp, vp]),
@@ -350,6 +353,13 @@ class PathTracer:
     def block_costs_range_async(self, pilot_spp: int, costs_dev_ptr: int, first_block: int, n_blocks: int, stream: int = 0) -> None:
         """Pilot pass over blocks [first_block, first_block + n_blocks) of the row-major block grid only."""
         self._ck(self.lib.ptcore_block_costs_range_async(self.h, pilot_spp, costs_dev_ptr, first_block, n_blocks, stream or None))
+
+    def render_keyed_async(self, accum_dev_ptr: int, n_chunks: int, first_chunk: int = 0, chunk_step: int = 1, blocks_dev_ptr: int = 0, n_blocks: int = 0, stream: int = 0) -> None:
+        """PT_RNG_SAMPLE_KEYED: chunks first_chunk, first_chunk + chunk_step, ... of every pixel (of the listed blocks) into accum[chunk][pixel][3]."""
+        self._ck(self.lib.ptcore_render_keyed_async(self.h, blocks_dev_ptr or None, n_blocks, accum_dev_ptr, n_chunks, first_chunk, chunk_step, stream or None))
+
+    def resolve_keyed_async(self, accum_dev_ptr: int, n_chunks: int, stream: int = 0) -> None:
+        self._ck(self.lib.ptcore_resolve_keyed_async(self.h, accum_dev_ptr, n_chunks, stream or None))
 
     def set_retire_log(self, log_dev_ptr: int, n_warps: int) -> None:
         self._ck(self.lib.ptcore_set_retire_log(self.h, log_dev_ptr or None, n_warps))

@@ -96,6 +96,10 @@ struct RenderParams {
     int32_t pool_period;   // traverse iterations between two rounds of housekeeping (retire finished rays, pull new ones): 1, 2, 4 or 8
     int32_t lanes_per_warp;  // wavefront kernel: lanes of a warp that take pixels (32 = all; fewer = shorter chains per pixel, see sched)
     int32_t pad4;
+    // PT_RNG_SAMPLE_KEYED (ptcore_render_keyed_async): partial colour sums, [chunk][pixel][3] floats; this launch renders chunks
+    // keyed_first, keyed_first + keyed_step, ... (keyed_my_chunks of them) of keyed_chunk_spp samples each
+    float *keyed_accum;
+    uint32_t keyed_chunk_spp, keyed_first, keyed_step, keyed_my_chunks;
     unsigned long long *retire_log;  // optional (ptcore_set_retire_log): [2 * global warp index] = globaltimer at warp start, [+1] = at warp exit
     uint32_t retire_log_warps;       // capacity of retire_log in warps
     uint32_t pad5;

@@ -182,11 +182,17 @@ __global__ void __launch_bounds__(kBlockThreads) pt_persistent_kernel(const __gr
 // waiting the warp leaves TRAVERSE, shades exactly those lanes (they get their bounce ray or the next camera
 // ray) and re-enters with the unfinished lanes resuming where they stopped — warp-level ray compaction without
 // moving any state between lanes, which the one-XORWOW-stream-per-pixel contract forbids.
-template <bool SPHERES, bool RTOW, bool COUNT, int NODES>  // NODES: 0 = 64-byte two-child nodes, 1 = four-wide nodes, 2 = 32-byte quantised two-child nodes, 3 = the same in shared memory
+// KEYED (PT_OPT_RNG_MODE = PT_RNG_SAMPLE_KEYED): the XORWOW stream is keyed by (pixel, sample) instead of by pixel — sample s of
+// pixel p draws from curand_init(1984 + p + s * W * H, 0, 0) — so the samples of a pixel no longer form one sequential chain.  A
+// work item is then one CHUNK of a pixel's samples; its partial colour sum goes to accum[chunk][pixel] and pt_resolve_keyed_kernel
+// adds the chunks in order.  Same integrand, same estimator, different random numbers: parity with the reference is statistical
+// in this mode (converged RMSE), which is why it is never the default.
+template <bool SPHERES, bool RTOW, bool COUNT, int NODES, bool KEYED = false>  // NODES: 0 = 64-byte two-child nodes, 1 = four-wide nodes, 2 = 32-byte quantised two-child nodes, 3 = the same in shared memory
 __device__ __forceinline__ void wavefront_body(const RenderParams &p, const uint32_t smem_nodes) {
     constexpr bool WIDE = NODES == 1, QUANT = NODES >= 2, SMEM = NODES == 3;
     const unsigned lane = threadIdx.x & 31u;
-    const uint32_t total_items = work_total(p);
+    const uint32_t total_items = KEYED ? work_total(p) * p.keyed_my_chunks : work_total(p);
+    uint32_t sample_end = p.spp;  // KEYED: first sample after this lane's chunk
     const int refill_at = p.refill_at;
     const int node_burst = p.node_burst;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -209,8 +215,14 @@ __device__ __forceinline__ void wavefront_body(const RenderParams &p, const uint
 
     for (;;) {
         // ---------------- GENERATE / COMPACT ----------------
-        if (!have_path && have_pixel && samples_done == p.spp) {
-            finish_pixel(p, px, py, pixel_index, col, pixel_rays);
+        if (!have_path && have_pixel && samples_done == (KEYED ? sample_end : p.spp)) {
+            if (KEYED) {
+                const uint32_t chunk = (sample_end - 1u) / p.keyed_chunk_spp;
+                float *a = p.keyed_accum + ((size_t)chunk * (size_t)(p.width * p.height) + (size_t)pixel_index) * 3;
+                a[0] = col.x; a[1] = col.y; a[2] = col.z;
+            } else {
+                finish_pixel(p, px, py, pixel_index, col, pixel_rays);
+            }
             have_pixel = false;
         }
         const bool need = !retired && !have_pixel;
@@ -222,21 +234,34 @@ __device__ __forceinline__ void wavefront_body(const RenderParams &p, const uint
             base = __shfl_sync(kFullMask, base, leader);
             if (need) {
                 const uint32_t item = base + (uint32_t)__popc(need_mask & ((1u << lane) - 1u));
+                uint32_t pitem = item, chunk = 0;
+                if (KEYED) {  // 32 consecutive items = the 32 pixels of one block in ONE chunk; a block's chunks follow each other
+                    const uint32_t bi = item >> 5, k = bi % p.keyed_my_chunks;
+                    pitem = ((bi / p.keyed_my_chunks) << 5) | (item & 31u);
+                    chunk = p.keyed_first + k * p.keyed_step;
+                }
                 if (item >= total_items) {
                     retired = true;
-                } else if (work_to_pixel(p, item, px, py)) {
+                } else if (work_to_pixel(p, pitem, px, py)) {
                     pixel_index = ((int)p.height - py - 1) * (int)p.width + px;
-                    rng_init(rng, (unsigned long long)(long long)(1984 + pixel_index));
                     col = f3(0.f, 0.f, 0.f);
-                    samples_done = 0;
+                    if (KEYED) {
+                        samples_done = chunk * p.keyed_chunk_spp;
+                        sample_end = min(p.spp, samples_done + p.keyed_chunk_spp);
+                        have_pixel = samples_done < sample_end;
+                    } else {
+                        rng_init(rng, (unsigned long long)(long long)(1984 + pixel_index));
+                        samples_done = 0;
+                        have_pixel = true;
+                    }
                     pixel_rays = 0;
-                    have_pixel = true;
                 }
             }
         }
         if (__all_sync(kFullMask, retired)) break;
 
-        if (!have_path && have_pixel && samples_done < p.spp) {
+        if (!have_path && have_pixel && samples_done < (KEYED ? sample_end : p.spp)) {
+            if (KEYED) rng_init(rng, 1984ull + (unsigned long long)pixel_index + (unsigned long long)samples_done * (unsigned long long)(p.width * p.height));
             float u = float(px + rng_uniform(rng)) / float(p.width);
             float v = float(py + rng_uniform(rng)) / float(p.height);
             camera_ray(p.cam, u, v, ro, rd);
@@ -326,9 +351,9 @@ __device__ __forceinline__ void wavefront_body(const RenderParams &p, const uint
     if (p.retire_log && lane == 0 && warp_global < p.retire_log_warps) p.retire_log[2 * warp_global + 1] = global_timer_ns();
 }
 
-template <bool SPHERES, bool RTOW, bool COUNT, int NODES>
+template <bool SPHERES, bool RTOW, bool COUNT, int NODES, bool KEYED = false>
 __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __grid_constant__ RenderParams p) {
-    wavefront_body<SPHERES, RTOW, COUNT, NODES>(p, 0u);
+    wavefront_body<SPHERES, RTOW, COUNT, NODES, KEYED>(p, 0u);
 }
 
 // The same kernel as ONE 1024-thread CTA per SM whose warps share a copy of the quantised node array in shared memory (scenes
@@ -337,12 +362,24 @@ __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __
 // at 86 % hit rate and 18 active lanes is nearly always (profiles/r01_ncu_wavefront_final_1080p_1024spp.txt: 3.0 of the 10.5
 // cycles between two issues of a warp are long-scoreboard waits).
 constexpr int kSmemKernelThreads = 1024;
-template <bool SPHERES, bool RTOW, bool COUNT>
+template <bool SPHERES, bool RTOW, bool COUNT, bool KEYED = false>
 __global__ void __launch_bounds__(kSmemKernelThreads, 1) pt_wavefront_smem_kernel(const __grid_constant__ RenderParams p, const int32_t n_nodes) {
     extern __shared__ uint4 smem_nodesq[];
     for (int i = (int)threadIdx.x; i < n_nodes * 2; i += kSmemKernelThreads) smem_nodesq[i] = __ldg(&p.scene.nodesq[i]);
     __syncthreads();
-    wavefront_body<SPHERES, RTOW, COUNT, 3>(p, (uint32_t)__cvta_generic_to_shared(smem_nodesq));
+    wavefront_body<SPHERES, RTOW, COUNT, 3, KEYED>(p, (uint32_t)__cvta_generic_to_shared(smem_nodesq));
+}
+
+// PT_RNG_SAMPLE_KEYED: adds the chunk sums of every pixel in chunk order and stores the pixel (quantiser + RGB8 + I420 as always)
+__global__ void pt_resolve_keyed_kernel(const __grid_constant__ RenderParams p, const uint32_t n_chunks) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, npix = p.width * p.height;
+    if (i >= npix) return;
+    float3 col = f3(0.f, 0.f, 0.f);
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const float *a = p.keyed_accum + ((size_t)c * npix + i) * 3;
+        col = col + f3(a[0], a[1], a[2]);
+    }
+    store_pixel(p, (int)i, col);
 }
 
 // Once per scene upload: the shading frame of every triangle (hit_record.normal, triangle.h:103, and the onb that

@@ -77,6 +77,8 @@ struct ptcore {
     int node_format = PT_NODES_AUTO;
     int sah_isect_x100 = 120;
     int lanes_per_warp = 32;
+    int rng_mode = PT_RNG_STREAM;
+    int rng_chunks = 16;
     bool sticky_textures = true;
     unsigned long long *retire_log = nullptr;
     uint32_t retire_log_warps = 0;
@@ -267,6 +269,42 @@ cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaS
         else pt_wavefront_kernel<S, R, C, 0><<<grid, kBlockThreads, 0, stream>>>(rp);
     }
     return cudaGetLastError();
+}
+
+// PT_RNG_SAMPLE_KEYED launches: the wavefront kernel with KEYED = true (shared-memory nodes when they fit, else quantised or float
+// nodes through L1); the test counters are not offered in this mode
+template <bool S, bool R>
+cudaError_t launch_keyed_variant(ptcore *h, const RenderParams &rp, cudaStream_t stream) {
+    const uint32_t total = rp.tiles.first_item[rp.tiles.n] * rp.keyed_my_chunks;
+    if (total == 0) return cudaSuccess;
+    if (h->smem_nodes && use_quantised(h) && (size_t)h->blob.n_nodes * 32 <= (size_t)h->smem_nodes_max_bytes) {
+        const size_t bytes = (size_t)h->blob.n_nodes * 32;
+        cudaError_t e = cudaFuncSetAttribute(pt_wavefront_smem_kernel<S, R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        uint32_t grid = (uint32_t)h->sm_count;
+        const uint32_t needed = (total + kSmemKernelThreads - 1) / kSmemKernelThreads;
+        if (grid > needed) grid = needed;
+        pt_wavefront_smem_kernel<S, R, false, true><<<grid, kSmemKernelThreads, bytes, stream>>>(rp, h->blob.n_nodes);
+        return cudaGetLastError();
+    }
+    int occ = 0;
+    cudaError_t e = use_quantised(h) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_wavefront_kernel<S, R, false, 2, true>, kBlockThreads, 0)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_wavefront_kernel<S, R, false, 0, true>, kBlockThreads, 0);
+    if (e != cudaSuccess) return e;
+    uint32_t grid = (uint32_t)h->sm_count * (uint32_t)std::max(1, occ);
+    const uint32_t needed = (total + kBlockThreads - 1) / kBlockThreads;
+    if (grid > needed) grid = needed;
+    if (use_quantised(h)) pt_wavefront_kernel<S, R, false, 2, true><<<grid, kBlockThreads, 0, stream>>>(rp);
+    else pt_wavefront_kernel<S, R, false, 0, true><<<grid, kBlockThreads, 0, stream>>>(rp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_keyed(ptcore *h, const RenderParams &rp, cudaStream_t stream) {
+    const bool S = h->blob.has_spheres, R = h->blob.has_rtow;
+    if (!S && !R) return launch_keyed_variant<false, false>(h, rp, stream);
+    if (!S && R) return launch_keyed_variant<false, true>(h, rp, stream);
+    if (S && !R) return launch_keyed_variant<true, false>(h, rp, stream);
+    return launch_keyed_variant<true, true>(h, rp, stream);
 }
 
 cudaError_t launch(ptcore *h, const RenderParams &rp, cudaStream_t stream) {
@@ -813,6 +851,14 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
             h->lanes_per_warp = (int)value;
             return PT_OK;
         case PT_OPT_STICKY_TEXTURES: h->sticky_textures = value != 0; return PT_OK;
+        case PT_OPT_RNG_MODE:
+            if (value != PT_RNG_STREAM && value != PT_RNG_SAMPLE_KEYED) return fail(h, PT_ERR_INVALID_ARGUMENT, "unknown rng mode");
+            h->rng_mode = (int)value;
+            return PT_OK;
+        case PT_OPT_RNG_CHUNKS:
+            if (value < 1 || value > 4096) return fail(h, PT_ERR_INVALID_ARGUMENT, "rng_chunks must be in [1, 4096]");
+            h->rng_chunks = (int)value;
+            return PT_OK;
         case PT_OPT_WATCHDOG:
             if (value < 0 || value > 0xffffffffll) return fail(h, PT_ERR_INVALID_ARGUMENT, "watchdog must fit 32 bits");
             h->watchdog = (uint32_t)value;
@@ -884,6 +930,93 @@ int ptcore_block_costs_range_async(ptcore_t *h, uint32_t pilot_spp, uint32_t *co
     return block_costs_range(h, pilot_spp, costs_dev, first_block, n_blocks, false, stream);
 }
 
+static int keyed_identity_blocks(ptcore_t *h) {
+    const uint32_t bw = (h->fb_w + 7) / 8, bh = (h->fb_h + 3) / 4, n = bw * bh;
+    if (h->ident_blocks_n == n && h->ident_bw == bw) return PT_OK;
+    std::vector<uint32_t> ident(n);
+    for (uint32_t by = 0; by < bh; by++)
+        for (uint32_t bx = 0; bx < bw; bx++) ident[by * bw + bx] = bx | (by << 16);
+    cudaFree(h->ident_blocks);
+    h->ident_blocks = nullptr;
+    h->ident_blocks_n = 0;
+    PT_CUDA(h, cudaMalloc(&h->ident_blocks, sizeof(uint32_t) * n));
+    PT_CUDA(h, cudaMemcpy(h->ident_blocks, ident.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+    h->ident_blocks_n = n;
+    h->ident_bw = bw;
+    return PT_OK;
+}
+
+int ptcore_render_keyed_async(ptcore_t *h, const uint32_t *blocks_dev, uint32_t n_blocks, float *accum_dev, uint32_t n_chunks, uint32_t first_chunk, uint32_t chunk_step,
+                              void *stream) {
+    if (!h || !accum_dev || n_chunks == 0 || chunk_step == 0) return fail(h, PT_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (!h->have_scene) return fail(h, PT_ERR_NO_SCENE, "no scene uploaded");
+    if (!h->fb_rgb) return fail(h, PT_ERR_NO_FRAMEBUFFER, "no framebuffer bound");
+    if (!h->have_cam) return fail(h, PT_ERR_INVALID_ARGUMENT, "no camera set");
+    if (h->depth == 0) return fail(h, PT_ERR_UNSUPPORTED, "keyed rendering needs recursion depth >= 1");
+    PT_CUDA(h, cudaSetDevice(h->device));
+    if (!blocks_dev) {
+        int rc = keyed_identity_blocks(h);
+        if (rc != PT_OK) return rc;
+        blocks_dev = h->ident_blocks;
+        n_blocks = h->ident_blocks_n;
+    }
+    if (first_chunk >= n_chunks || n_blocks == 0) return PT_OK;
+    const uint32_t my_chunks = (n_chunks - first_chunk + chunk_step - 1) / chunk_step;
+    if ((uint64_t)n_blocks * 32ull * my_chunks > 0xfffffff0ull) return fail(h, PT_ERR_UNSUPPORTED, "too many work items");
+    RenderParams rp;
+    memset(&rp, 0, sizeof rp);
+    rp.scene = h->dscene;
+    rp.cam = h->cam;
+    rp.width = h->fb_w;
+    rp.height = h->fb_h;
+    rp.spp = h->spp;
+    rp.depth = h->depth;
+    rp.refill_at = h->refill_at;
+    rp.node_burst = h->node_burst;
+    rp.lanes_per_warp = h->lanes_per_warp;
+    rp.retire_log = h->retire_log;
+    rp.retire_log_warps = h->retire_log_warps;
+    rp.fb_rgb = h->fb_rgb;
+    rp.fb_yuv = h->fb_yuv;
+    rp.counters = h->d_counters;
+    rp.block_list = blocks_dev;
+    rp.n_blocks = n_blocks;
+    rp.tiles.n = 1;
+    rp.tiles.first_item[0] = 0;
+    rp.tiles.first_item[1] = n_blocks * 32u;
+    rp.keyed_accum = accum_dev;
+    rp.keyed_chunk_spp = (h->spp + n_chunks - 1) / n_chunks;
+    rp.keyed_first = first_chunk;
+    rp.keyed_step = chunk_step;
+    rp.keyed_my_chunks = my_chunks;
+    uint64_t seq = h->launch_seq.fetch_add(1);
+    rp.work_counter = h->d_work + (seq % kCounterRing);
+    PT_CUDA(h, cudaMemsetAsync(rp.work_counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
+    PT_CUDA(h, launch_keyed(h, rp, (cudaStream_t)stream));
+    h->samples.fetch_add((uint64_t)n_blocks * 32u * (uint64_t)std::min<uint64_t>(h->spp, (uint64_t)rp.keyed_chunk_spp * my_chunks));
+    h->launches.fetch_add(1);
+    return PT_OK;
+}
+
+int ptcore_resolve_keyed_async(ptcore_t *h, const float *accum_dev, uint32_t n_chunks, void *stream) {
+    if (!h || !accum_dev || n_chunks == 0) return fail(h, PT_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (!h->fb_rgb) return fail(h, PT_ERR_NO_FRAMEBUFFER, "no framebuffer bound");
+    PT_CUDA(h, cudaSetDevice(h->device));
+    RenderParams rp;
+    memset(&rp, 0, sizeof rp);
+    rp.width = h->fb_w;
+    rp.height = h->fb_h;
+    rp.spp = h->spp;
+    rp.fb_rgb = h->fb_rgb;
+    rp.fb_yuv = h->fb_yuv;
+    rp.keyed_accum = const_cast<float *>(accum_dev);
+    const uint32_t npix = h->fb_w * h->fb_h;
+    pt_resolve_keyed_kernel<<<(npix + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rp, n_chunks);
+    PT_CUDA(h, cudaGetLastError());
+    h->launches.fetch_add(1);
+    return PT_OK;
+}
+
 int ptcore_set_retire_log(ptcore_t *h, uint64_t *log_dev, uint32_t n_warps) {
     if (!h) return PT_ERR_INVALID_ARGUMENT;
     h->retire_log = reinterpret_cast<unsigned long long *>(log_dev);
@@ -927,8 +1060,21 @@ int ptcore_render_frame_host(ptcore_t *h, uint32_t width, uint32_t height, uint8
     h->fb_yuv = yuv_host ? h->own_yuv : nullptr;
     h->fb_w = width;
     h->fb_h = height;
-    PtTile t{(int32_t)width, (int32_t)height, 0, 0};
-    int rc = render_tiles(h, &t, 1, nullptr);
+    int rc;
+    if (h->rng_mode == PT_RNG_SAMPLE_KEYED && h->depth > 0) {
+        const uint32_t n_chunks = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)h->rng_chunks, h->spp));
+        float *accum = nullptr;
+        const size_t bytes = (size_t)n_chunks * px * 3 * sizeof(float);
+        cudaError_t e = cudaMalloc(&accum, bytes);
+        if (e == cudaSuccess) e = cudaMemsetAsync(accum, 0, bytes, nullptr);
+        rc = e == cudaSuccess ? ptcore_render_keyed_async(h, nullptr, 0, accum, n_chunks, 0, 1, nullptr) : fail(h, (int)e, std::string("keyed accumulation buffer: ") + cudaGetErrorString(e));
+        if (rc == PT_OK) rc = ptcore_resolve_keyed_async(h, accum, n_chunks, nullptr);
+        cudaStreamSynchronize(nullptr);
+        cudaFree(accum);
+    } else {
+        PtTile t{(int32_t)width, (int32_t)height, 0, 0};
+        rc = render_tiles(h, &t, 1, nullptr);
+    }
     h->fb_rgb = srgb; h->fb_yuv = syuv; h->fb_w = sw; h->fb_h = sh;
     if (rc != PT_OK) return rc;
     PT_CUDA(h, cudaMemcpyAsync(rgb_host, h->own_rgb, px * 3, cudaMemcpyDeviceToHost, nullptr));

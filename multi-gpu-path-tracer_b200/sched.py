@@ -151,3 +151,49 @@ class RankRenderer:
         self.launches += 2
         self.stage_events.append([("pilot", ev[0], ev[1]), ("sort", ev[1], ev[2]), ("render", ev[2], ev[3]), ("gather", ev[3], ev[4])])
         cur.wait_stream(s)
+
+    def render_frame_keyed(self, rank: int, world: int, n_chunks: int = 16, pilot_spp: int = 4, gather: bool = True, emulated: bool = False) -> None:
+        """PT_RNG_SAMPLE_KEYED frame (capi.PT_RNG_SAMPLE_KEYED; parity is statistical in this mode, so it is never the bench line).
+
+        The stream is keyed by (pixel, sample), so a pixel's spp samples are cut into n_chunks independent work items.  Rank r
+        traces chunks r, r + world, ... of EVERY pixel — statistically identical shares, no pilot pass needed for balance between
+        ranks; within a GPU the blocks are taken most-expensive-first (same cost map as the stream mode).  The chunk sums travel as
+        one float reduce (every entry is written by exactly one rank: the sum is exact) and rank 0 adds the chunks of every pixel in
+        chunk order: the image does not depend on world, on n_chunks' assignment to ranks or on launch order.
+        """
+        import torch.distributed as dist
+        cur = torch.cuda.current_stream(self.device)
+        s = self.streams[0]
+        s.wait_stream(cur)
+        bw, bh = (self.width + 7) // 8, (self.height + 3) // 4
+        n = bw * bh
+        npix = self.width * self.height
+        if getattr(self, "costs", None) is None or self.costs.numel() != n:
+            self.costs = torch.zeros(n, dtype=torch.int32, device=self.device)
+        if getattr(self, "accum", None) is None or self.accum.numel() != n_chunks * npix * 3:
+            self.accum = torch.zeros(n_chunks * npix * 3, dtype=torch.float32, device=self.device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        distributed = world > 1 and not emulated
+        with torch.cuda.stream(s):
+            ev[0].record(s)
+            self.accum.zero_()
+            if distributed:
+                per = (n + world - 1) // world
+                self.pt.block_costs_range_async(pilot_spp, self.costs.data_ptr(), rank * per, per, s.cuda_stream)
+                dist.all_reduce(self.costs, op=dist.ReduceOp.SUM)
+            else:
+                self.pt.block_costs_async(pilot_spp, self.costs.data_ptr(), s.cuda_stream)
+            ev[1].record(s)
+            order = torch.argsort(self.costs, descending=True, stable=True)
+            self.blocks = ((order % bw) | ((order // bw) << 16)).to(torch.int32).contiguous()
+            ev[2].record(s)
+            self.pt.render_keyed_async(self.accum.data_ptr(), n_chunks, rank, world, self.blocks.data_ptr(), int(self.blocks.numel()), s.cuda_stream)
+            ev[3].record(s)
+            if distributed and gather:
+                dist.reduce(self.accum, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0 or not distributed:
+                self.pt.resolve_keyed_async(self.accum.data_ptr(), n_chunks, s.cuda_stream)
+            ev[4].record(s)
+        self.launches += 3
+        self.stage_events.append([("pilot", ev[0], ev[1]), ("sort", ev[1], ev[2]), ("render", ev[2], ev[3]), ("gather", ev[3], ev[4])])
+        cur.wait_stream(s)

@@ -24,6 +24,7 @@ IMAGES = [
     ("duck_64x48_s16_d3_cam", 64, 48, 16, 3, ["--cam", "-120", "40", "-300", "0.25", "-0.1", "-1", "60", "80"]),
     ("duck_320x180_s16_d10", 320, 180, 16, 10, []),
     ("duck_37x23_s5_d1", 37, 23, 5, 1, []),
+    ("duck_64x36_s4096_d10", 64, 36, 4096, 10, []),  # converged frame: gate A at 4096 spp and the RMSE bound of the keyed RNG mode
 ]
 
 

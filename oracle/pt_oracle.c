@@ -668,6 +668,12 @@ pto_vec3 pto_ray_color(const pto_world *w, pto_vec3 o, pto_vec3 d, uint32_t dept
     return ray_color(w, o, d, depth, &c);
 }
 
+/* Builder-defined mode with no counterpart in the reference (ptcore.h: PT_RNG_SAMPLE_KEYED): n_chunks > 0 keys the XORWOW stream by
+ * (pixel, sample) — sample s of pixel p draws from curand_init(1984 + p + s * W * H, 0, 0) — and adds the samples chunk by chunk
+ * (ceil(spp / n_chunks) samples each), then the chunk sums in order, as the CUDA core does.  0 = the reference's streams (default). */
+static uint32_t g_keyed_chunks = 0;
+void pto_set_keyed_chunks(uint32_t n_chunks) { g_keyed_chunks = n_chunks; }
+
 int pto_render(const pto_world *w, const PtCamera *cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t depth,
                int32_t ox, int32_t oy, int32_t tw, int32_t th, uint8_t *rgb, uint8_t *yuv, float *accum, pto_stats *st, int threads) {
     if (!w || !cam || !rgb || width == 0 || height == 0) return -1;
@@ -694,13 +700,21 @@ int pto_render(const pto_world *w, const PtCamera *cam, uint32_t width, uint32_t
                 pto_rng_init(&rs, (uint64_t)(int64_t)(1984 + pixel_index)); /* render_init, :54 */
                 rng_ctx c = {&rs, &local, NULL, 0, 0, 0.f};
                 v3 col = V(0, 0, 0);
+                const uint32_t chunk_spp = g_keyed_chunks ? (spp + g_keyed_chunks - 1) / g_keyed_chunks : 0;
+                v3 part = V(0, 0, 0);
                 for (uint32_t s = 0; s < spp; s++) {
+                    if (chunk_spp) pto_rng_init(&rs, 1984ull + (uint64_t)pixel_index + (uint64_t)s * (uint64_t)(width * height));
                     float u = (float)(x + U(&c)) / (float)width;
                     float v = (float)(y + U(&c)) / (float)height;
                     v3 ro, rd;
                     camera_get_ray(&cp, u, v, &ro, &rd);
                     local.samples++;
-                    col = vadd(col, ray_color(w, ro, rd, depth, &c));
+                    if (chunk_spp) {
+                        part = vadd(part, ray_color(w, ro, rd, depth, &c));
+                        if ((s + 1) % chunk_spp == 0 || s + 1 == spp) { col = vadd(col, part); part = V(0, 0, 0); }
+                    } else {
+                        col = vadd(col, ray_color(w, ro, rd, depth, &c));
+                    }
                 }
                 float cc[3] = {col.x, col.y, col.z};
                 uint8_t q[3];

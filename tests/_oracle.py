@@ -85,8 +85,9 @@ class Oracle:
         w = self.lib.pto_world_create(C.byref(d))
         return w
 
-    def render(self, scene_or_world, width, height, spp, depth, camera=None, rect=None, threads=0, want_accum=False):
-        """Returns (rgb[h,w,3] u8, yuv[w*h*3/2] u8, stats dict[, accum])."""
+    def render(self, scene_or_world, width, height, spp, depth, camera=None, rect=None, threads=0, want_accum=False, keyed_chunks=0):
+        """Returns (rgb[h,w,3] u8, yuv[w*h*3/2] u8, stats dict[, accum]).  keyed_chunks > 0: the (pixel, sample)-keyed RNG mode."""
+        self.lib.pto_set_keyed_chunks(keyed_chunks)
         own = not isinstance(scene_or_world, int)
         w = self.world(scene_or_world) if own else scene_or_world
         cam = self.ptb.make_camera(**{**self.ptb.DEFAULT_CAMERA, **(camera or {})})

@@ -468,3 +468,71 @@ def test_pool_kernel_and_shared_memory_nodes_equal_the_wavefront_kernel(tracer, 
     tracer.set_option(ptb.PT_OPT_KERNEL, ptb.PT_KERNEL_PERSISTENT)
     assert np.array_equal(fb.cpu().numpy().reshape(h, w, 3), full)
     assert np.array_equal(fy.cpu().numpy(), yfull)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# PT_RNG_SAMPLE_KEYED: the throughput mode whose stream is keyed by (pixel, sample).  Not comparable with the reference sample
+# for sample (different random numbers); checked (1) against the CPU oracle running the SAME keyed streams, gate-B tolerance,
+# (2) for its exact invariants — the image does not depend on how chunks are split over launches / ranks or on the kernel
+# variant — and (3) converged: RMSE <= 1.0 / 255 against the reference's OWN CUDA renderer at 4096 spp (fixture rendered by
+# oracle/_ref/ref_gpu on a B200, oracle/make_golden_gpu.py) and against our stream-faithful mode.
+# ---------------------------------------------------------------------------------------------------------------------------
+def _render_keyed(tracer, ptb, w, h, n_chunks, splits=((0, 1),)):
+    import torch
+    fb = torch.zeros(h * w * 3, dtype=torch.uint8, device="cuda")
+    fy = torch.zeros(h * w * 3 // 2, dtype=torch.uint8, device="cuda")
+    acc = torch.zeros(n_chunks * w * h * 3, dtype=torch.float32, device="cuda")
+    tracer.bind_framebuffer(fb.data_ptr(), fy.data_ptr(), w, h)
+    for first, step in splits:
+        tracer.render_keyed_async(acc.data_ptr(), n_chunks, first, step)
+    tracer.resolve_keyed_async(acc.data_ptr(), n_chunks)
+    tracer.wait()
+    return fb.cpu().numpy().reshape(h, w, 3), fy.cpu().numpy()
+
+
+def test_keyed_rng_mode_matches_the_oracle_running_the_same_streams_and_is_split_invariant(tracer, oracle, duck, ptb):
+    w, h, spp, depth, n_chunks = 160, 90, 24, 10, 6
+    tracer.upload_scene(duck)
+    tracer.set_camera()
+    tracer.set_params(spp, depth)
+    one, yone = _render_keyed(tracer, ptb, w, h, n_chunks)
+    ref, _, _ = oracle.render(duck, w, h, spp, depth, keyed_chunks=n_chunks)
+    print(check(one, ref, spp))
+    stream_mode, _ = tracer.render_frame_host(w, h)
+    assert not np.array_equal(one, stream_mode)  # other random numbers ...
+    assert abs(float(one.mean()) - float(stream_mode.mean())) < 0.02 * float(stream_mode.mean())  # ... same estimator
+    # two / three "ranks" (chunks r, r + N, ...), in any order, and the other kernel variant: the same bytes
+    two, ytwo = _render_keyed(tracer, ptb, w, h, n_chunks, splits=((1, 2), (0, 2)))
+    three, _ = _render_keyed(tracer, ptb, w, h, n_chunks, splits=((2, 3), (0, 3), (1, 3)))
+    tracer.set_option(ptb.PT_OPT_SMEM_NODES, 0)
+    other, _ = _render_keyed(tracer, ptb, w, h, n_chunks)
+    tracer.set_option(ptb.PT_OPT_SMEM_NODES, 1)
+    for img in (two, three, other):
+        assert np.array_equal(one, img)
+    assert np.array_equal(yone, ytwo)
+    # the whole-frame convenience call with PT_OPT_RNG_MODE
+    tracer.set_option(ptb.PT_OPT_RNG_MODE, ptb.PT_RNG_SAMPLE_KEYED)
+    tracer.set_option(ptb.PT_OPT_RNG_CHUNKS, n_chunks)
+    host, _ = tracer.render_frame_host(w, h)
+    tracer.set_option(ptb.PT_OPT_RNG_MODE, ptb.PT_RNG_STREAM)
+    assert np.array_equal(one, host)
+
+
+def test_keyed_rng_mode_converges_to_the_reference_renderer(tracer, duck, ptb):
+    """North-star check 2 for the keyed mode: >= 4096 spp against Oracle G at >= 4096 spp, RMSE <= 1.0 / 255."""
+    name = "duck_64x36_s4096_d10"
+    if name not in REF_GPU_META:
+        pytest.skip("fixture ref_gpu_duck_64x36_s4096_d10 not generated yet (oracle/make_golden_gpu.py on a GPU box)")
+    m = REF_GPU_META[name]
+    w, h, spp, depth = m["width"], m["height"], m["spp"], m["depth"]
+    ref = np.array(Image.open(GOLD / f"ref_gpu_{name}.png").convert("RGB")).astype(np.float64)
+    tracer.upload_scene(duck)
+    tracer.set_camera()
+    tracer.set_params(spp, depth)
+    stream_mode, _ = tracer.render_frame_host(w, h)
+    assert np.array_equal(stream_mode, ref.astype(np.uint8))  # gate A at 4096 spp: the stream-faithful mode IS the reference image
+    keyed, _ = _render_keyed(tracer, ptb, w, h, 32)
+    d = keyed.astype(np.float64) - ref
+    rmse = float(np.sqrt((d ** 2).mean()))
+    print(dict(rmse=rmse, mean_diff=float(d.mean()), max=float(np.abs(d).max())))
+    assert rmse <= 1.0 and abs(float(d.mean())) <= 0.1
