@@ -419,7 +419,7 @@ def main():
             kms = float(kt[0])
         keyed = {"value": WIDTH * HEIGHT * spp * args.keyed_steps / (kms / 1e3) / 1e6, "unit": "Msamples/s", "ms_per_step": kms / args.keyed_steps, "steps": args.keyed_steps,
                  "chunks_per_pixel": args.keyed_chunks, "stages_ms": kstages,
-                 "rng": "XORWOW keyed by (pixel, sample): curand_init(1984 + pixel + sample * W * H, 0, 0); parity with the reference is statistical in this mode (converged RMSE <= 1/255, tests/test_gpu_parity.py)",
+                 "rng": "XORWOW keyed by (pixel, sample): curand_init(splitmix64(1984 + pixel + sample * W * H), 0, 0); parity with the reference is statistical in this mode (converged RMSE <= 1/255, tests/test_gpu_parity.py)",
                  "parallelism": "rank r traces chunks r, r + N, ... of every pixel; one float reduce of the chunk sums; rank 0 adds them in chunk order"}
         rr.reset_stage_times()
 

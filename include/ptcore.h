@@ -125,7 +125,7 @@ enum {
                                 sequence exactly as the reference does (src/DevicePathTracer.h:54,80-87): bit-exact images, but a pixel's
                                 spp samples form ONE sequential chain */
     PT_RNG_SAMPLE_KEYED = 1  /* throughput mode: the stream is keyed by (pixel, sample): sample s of pixel p draws from
-                                curand_init(1984 + p + s * W * H, 0, 0); a pixel's samples are independent work items.  Same estimator,
+                                curand_init(splitmix64(1984 + p + s * W * H), 0, 0); a pixel's samples are independent work items.  Same estimator,
                                 different random numbers: parity is statistical (converged RMSE), images are still independent of how the
                                 work is split over launches and GPUs */
 };
@@ -205,6 +205,11 @@ int ptcore_block_costs_range_async(ptcore_t *h, uint32_t pilot_spp, uint32_t *co
 int ptcore_render_keyed_async(ptcore_t *h, const uint32_t *blocks_dev, uint32_t n_blocks, float *accum_dev, uint32_t n_chunks, uint32_t first_chunk, uint32_t chunk_step,
                               void *stream);
 int ptcore_resolve_keyed_async(ptcore_t *h, const float *accum_dev, uint32_t n_chunks, void *stream);
+/* Multi-GPU gather (replaces the page migration of the reference's cudaMallocManaged framebuffer, src/Framebuffer.h:27-35): copies the
+ * pixels of the listed 8x4 blocks (RGB, Y and the U / V samples they own) from the framebuffer bound to `h` into another frame of the
+ * same size — typically the master copy on GPU 0, written with peer stores over NVLink (peer access must be enabled by the caller) —
+ * on `stream`, i.e. right behind the ptcore_render_blocks_async that produced them.  dst_yuv may be NULL. */
+int ptcore_gather_blocks_async(ptcore_t *h, uint8_t *dst_rgb, uint8_t *dst_yuv, const uint32_t *blocks_dev, uint32_t n_blocks, void *stream);
 /* Measurement aid: while set, every warp of the wavefront kernel stores the GPU's nanosecond timer at its start and at its exit into
  * log_dev[2 * warp] / [2 * warp + 1] (DEVICE array of 2 * n_warps uint64; NULL switches it off).  bench.py derives from it when
  * 50 / 90 / 99 % of the lanes of a launch had retired. */

@@ -205,6 +205,7 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
         "ptcore_block_costs_async": (C.c_int, [vp, u32, vp, vp]),
         "ptcore_block_costs_range_async": (C.c_int, [vp, u32, vp, u32, u32, vp]),
         "ptcore_set_retire_log": (C.c_int, [vp, vp, u32]),
+        "ptcore_gather_blocks_async": (C.c_int, [vp, vp, vp, vp, u32, vp]),
         "ptcore_render_keyed_async": (C.c_int, [vp, vp, u32, vp, u32, u32, u32, vp]),
         "ptcore_resolve_keyed_async": (C.c_int, [vp, vp, u32, vp]),
         "ptcore_sync": (C.c_int, [vp, vp]),
@@ -360,6 +361,10 @@ class PathTracer:
 
     def resolve_keyed_async(self, accum_dev_ptr: int, n_chunks: int, stream: int = 0) -> None:
         self._ck(self.lib.ptcore_resolve_keyed_async(self.h, accum_dev_ptr, n_chunks, stream or None))
+
+    def gather_blocks_async(self, dst_rgb_ptr: int, dst_yuv_ptr: int, blocks_dev_ptr: int, n_blocks: int, stream: int = 0) -> None:
+        """Copies the listed blocks of the bound framebuffer into another frame of the same size (peer memory allowed)."""
+        self._ck(self.lib.ptcore_gather_blocks_async(self.h, dst_rgb_ptr, dst_yuv_ptr or None, blocks_dev_ptr, n_blocks, stream or None))
 
     def set_retire_log(self, log_dev_ptr: int, n_warps: int) -> None:
         self._ck(self.lib.ptcore_set_retire_log(self.h, log_dev_ptr or None, n_warps))

@@ -22,6 +22,17 @@ namespace ptc {
 constexpr int kBlockThreads = 128;
 constexpr unsigned kFullMask = 0xffffffffu;
 
+// PT_RNG_SAMPLE_KEYED: seed of sample s of pixel p = the counter 1984 + p + s * W * H passed through the splitmix64 finaliser, so that
+// the 64 bits from which curand_init(seed, 0, 0) derives the whole XORWOW state (curand_kernel.h:772-797) are well mixed although
+// consecutive counters differ in a few low bits only (the CPU checker restates the same function).
+__device__ __forceinline__ unsigned long long keyed_seed(uint32_t pixel_index, uint32_t sample, uint32_t npix) {
+    unsigned long long z = 1984ull + (unsigned long long)pixel_index + (unsigned long long)sample * (unsigned long long)npix;
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(kBlockThreads) pt_persistent_kernel(const __gr
 // ray) and re-enters with the unfinished lanes resuming where they stopped — warp-level ray compaction without
 // moving any state between lanes, which the one-XORWOW-stream-per-pixel contract forbids.
 // KEYED (PT_OPT_RNG_MODE = PT_RNG_SAMPLE_KEYED): the XORWOW stream is keyed by (pixel, sample) instead of by pixel — sample s of
-// pixel p draws from curand_init(1984 + p + s * W * H, 0, 0) — so the samples of a pixel no longer form one sequential chain.  A
+// pixel p draws from curand_init(splitmix64(1984 + p + s * W * H), 0, 0) — so the samples of a pixel no longer form one sequential chain.  A
 // work item is then one CHUNK of a pixel's samples; its partial colour sum goes to accum[chunk][pixel] and pt_resolve_keyed_kernel
 // adds the chunks in order.  Same integrand, same estimator, different random numbers: parity with the reference is statistical
 // in this mode (converged RMSE), which is why it is never the default.
@@ -261,7 +272,7 @@ __device__ __forceinline__ void wavefront_body(const RenderParams &p, const uint
         if (__all_sync(kFullMask, retired)) break;
 
         if (!have_path && have_pixel && samples_done < (KEYED ? sample_end : p.spp)) {
-            if (KEYED) rng_init(rng, 1984ull + (unsigned long long)pixel_index + (unsigned long long)samples_done * (unsigned long long)(p.width * p.height));
+            if (KEYED) rng_init(rng, keyed_seed((uint32_t)pixel_index, samples_done, p.width * p.height));
             float u = float(px + rng_uniform(rng)) / float(p.width);
             float v = float(py + rng_uniform(rng)) / float(p.height);
             camera_ray(p.cam, u, v, ro, rd);
@@ -506,6 +517,29 @@ __global__ void pt_trace_kernel(const __grid_constant__ RenderParams p, int px, 
     }
     *n_events = n;
     col_out[0] = col.x; col_out[1] = col.y; col_out[2] = col.z;
+}
+
+// Framebuffer gather of the multi-GPU path ("only the final framebuffer gather uses NCCL or P2P over NVLink"): copies the
+// pixels of the listed 8x4 blocks — RGB, Y, and the U / V samples their even-row / even-column pixels own (DevicePathTracer.h:107-119) —
+// from this GPU's private frame into the frame's master copy on another GPU, with peer stores over NVLink.  One thread per pixel.
+__global__ void pt_gather_blocks_kernel(uint8_t *__restrict__ dst_rgb, uint8_t *__restrict__ dst_yuv, const uint8_t *__restrict__ src_rgb, const uint8_t *__restrict__ src_yuv,
+                                        const uint32_t *__restrict__ blocks, uint32_t n_blocks, uint32_t width, uint32_t height) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((i >> 5) >= n_blocks) return;
+    const uint32_t b = __ldg(&blocks[i >> 5]), within = i & 31u;
+    const uint32_t x = (b & 0xffffu) * 8u + (within & 7u), y = (b >> 16) * 4u + (within >> 3);
+    if (x >= width || y >= height) return;
+    const uint32_t row = height - 1u - y, pix = row * width + x;  // RenderTask space is bottom-up, buffer row 0 is the top (:77-79)
+    dst_rgb[3 * (size_t)pix + 0] = src_rgb[3 * (size_t)pix + 0];
+    dst_rgb[3 * (size_t)pix + 1] = src_rgb[3 * (size_t)pix + 1];
+    dst_rgb[3 * (size_t)pix + 2] = src_rgb[3 * (size_t)pix + 2];
+    if (!dst_yuv || !src_yuv) return;
+    dst_yuv[pix] = src_yuv[pix];
+    if ((row & 1u) == 0 && (x & 1u) == 0) {
+        const uint32_t total = width * height, uvSize = total / 4, uv = (row / 2) * (width / 2) + (x / 2), limit = total + 2 * uvSize;
+        if (total + uv < limit) dst_yuv[total + uv] = src_yuv[total + uv];
+        if (total + uvSize + uv < limit) dst_yuv[total + uvSize + uv] = src_yuv[total + uvSize + uv];
+    }
 }
 
 // camera.h:21-36 evaluated with the device's own tanf / rsqrtf so the numbers are the ones the

@@ -1017,6 +1017,18 @@ int ptcore_resolve_keyed_async(ptcore_t *h, const float *accum_dev, uint32_t n_c
     return PT_OK;
 }
 
+int ptcore_gather_blocks_async(ptcore_t *h, uint8_t *dst_rgb, uint8_t *dst_yuv, const uint32_t *blocks_dev, uint32_t n_blocks, void *stream) {
+    if (!h || !dst_rgb || (n_blocks && !blocks_dev)) return fail(h, PT_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (!h->fb_rgb) return fail(h, PT_ERR_NO_FRAMEBUFFER, "no framebuffer bound");
+    if (n_blocks == 0 || dst_rgb == h->fb_rgb) return PT_OK;
+    PT_CUDA(h, cudaSetDevice(h->device));
+    const uint32_t threads = n_blocks * 32u;
+    pt_gather_blocks_kernel<<<(threads + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dst_rgb, dst_yuv, h->fb_rgb, h->fb_yuv, blocks_dev, n_blocks, h->fb_w, h->fb_h);
+    PT_CUDA(h, cudaGetLastError());
+    h->launches.fetch_add(1);
+    return PT_OK;
+}
+
 int ptcore_set_retire_log(ptcore_t *h, uint64_t *log_dev, uint32_t n_warps) {
     if (!h) return PT_ERR_INVALID_ARGUMENT;
     h->retire_log = reinterpret_cast<unsigned long long *>(log_dev);

@@ -1,7 +1,7 @@
 // ArgumentLoader.h — the reference's two positionals (src/ArgumentLoader.h:10-13: argv[1] = jobId,
 // argv[2] = modelPath, same defaults) plus optional flags, because every BASELINE config needs
 // parameters the reference can only receive over its websocket:
-//   --width N --height N --spp N --depth N --gpus N --streams N --block BXxBY --scheduler fsfl|dsfl|dsdl|dynamic
+//   --width N --height N --spp N --depth N --gpus N --streams N --block BXxBY --scheduler fsfl|dsfl|dsdl|dynamic|lpt
 //   --tile WxH --out file.ppm --frames N --vfov F --hfov F --lookfrom x,y,z --front x,y,z --show-tasks 0|1
 //   --monitor 0|1 (the reference's monitor thread: NVML figures + RENDER_STATS# messages every 500 ms)
 #pragma once
@@ -56,6 +56,7 @@ public:
                 else if (s == "dsfl") config.algorithmType = DSFL;
                 else if (s == "dsdl") config.algorithmType = DSDL;
                 else if (s == "dynamic") config.algorithmType = DYNAMIC;
+                else if (s == "lpt") config.algorithmType = LPT;
                 else throw std::runtime_error("unknown scheduler " + s);
             } else throw std::runtime_error("unknown argument " + a);
         }

@@ -25,7 +25,9 @@
 #include "RendererConfig.h"
 #include "cuda_utils.h"
 
+#include <atomic>
 #include <cstring>
+#include <iostream>
 #include <memory>
 #include <mutex>
 #include <vector>
@@ -142,7 +144,14 @@ public:
         } else {
             checkCudaErrors(cudaMalloc((void **)&priv_rgb_, px * 3));
             checkCudaErrors(cudaMalloc((void **)&priv_yuv_, px + 2 * (px / 4) + 2));
-            cudaError_t e = cudaDeviceEnablePeerAccess(framebuffer_->getMasterDevice(), 0);  // NVLink P2P; staged copy if unavailable
+            // NVLink P2P to the GPU that holds the frame's master copy.  Without it cudaMemcpy2DAsync(cudaMemcpyDefault) still works, but
+            // staged through host memory: say so (once per tracer) instead of silently running the slow path.
+            cudaError_t e = cudaDeviceEnablePeerAccess(framebuffer_->getMasterDevice(), 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                peerAccessFailures()++;
+                std::cerr << "DevicePathTracer: GPU " << device_idx_ << " cannot enable peer access to GPU " << framebuffer_->getMasterDevice() << " (" << cudaGetErrorString(e)
+                          << "): tile gather will be staged through host memory" << std::endl;
+            }
             if (e != cudaSuccess) cudaGetLastError();
             checkPtcore(core_, ptcore_bind_framebuffer(core_, priv_rgb_, priv_yuv_, res.width, res.height));
         }
@@ -164,7 +173,18 @@ public:
     }
 
     // additions
+    static std::atomic<int> &peerAccessFailures() {
+        static std::atomic<int> n{0};
+        return n;
+    }
     ptcore_t *core() { return core_; }
+    bool rendersIntoMaster() const { return rendersIntoMaster_; }
+    // makes sure the core has the camera the borrowed CameraConfig holds now (what renderTaskAsync does per task)
+    void syncCamera() {
+        std::lock_guard<std::mutex> lock(mu_);
+        cudaSetDevice(device_idx_);
+        if (!sameCamera(cameraConfig_, uploadedCamera_)) uploadCamera();
+    }
     int deviceIndex() const { return device_idx_; }
     PtStats stats() {
         PtStats s{};

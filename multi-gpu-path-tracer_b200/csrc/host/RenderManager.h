@@ -75,6 +75,7 @@ public:
             }
         }
         workers_.clear();
+        lptRelease();
         devicePathTracers_.clear();
         shutdown_ = false;
     }
@@ -203,7 +204,7 @@ public:
             mx = std::max(mx, w.ms);
         }
         stats_.imbalance = sum > 0 ? mx / (sum / (double)workers_.size()) : 1.0;
-        if (config_.showTasks && config_.algorithmType != SchedulingAlgorithmType::DYNAMIC) markTasks();
+        if (config_.showTasks && config_.algorithmType != SchedulingAlgorithmType::DYNAMIC && config_.algorithmType != SchedulingAlgorithmType::LPT) markTasks();
     }
 
     const FrameStats &lastFrameStats() const { return stats_; }
@@ -273,6 +274,13 @@ private:
         renderTasks_ = taskGen_.generateEqualTasks(threadCount_, taskLayout_, W, H);
         tiles_ = taskGen_.generateTiles((int)std::max(8u, config_.dynamicTileWidth), (int)std::max(4u, config_.dynamicTileHeight), W, H);
         frameCount_ = 0;
+        const uint32_t nBlocks = (uint32_t)((W + 7) / 8) * (uint32_t)((H + 3) / 4);
+        if (lpt_.size() != config_.gpuNumber) lpt_.resize(config_.gpuNumber);
+        if (lptHostCostsN_ < nBlocks) {
+            if (lptHostCosts_) cudaFreeHost(lptHostCosts_);
+            checkCudaErrors(cudaMallocHost((void **)&lptHostCosts_, sizeof(uint32_t) * nBlocks));
+            lptHostCostsN_ = nBlocks;
+        }
     }
 
     void workerMain(Worker *w) {
@@ -287,7 +295,10 @@ private:
             auto t0 = std::chrono::high_resolution_clock::now();
             DevicePathTracer &dpt = *devicePathTracers_[(size_t)w->device];
             w->tiles = 0;
-            if (config_.algorithmType == SchedulingAlgorithmType::DYNAMIC) {
+            if (config_.algorithmType == SchedulingAlgorithmType::LPT) {
+                // one worker per GPU drives the frame; further streams of the same GPU have nothing to add to one persistent launch
+                if (w->index % (int)config_.streamsPerGpu == 0) lptFrame(w, dpt);
+            } else if (config_.algorithmType == SchedulingAlgorithmType::DYNAMIC) {
                 const int n = (int)tiles_.size();
                 for (;;) {
                     // a slot is reusable once its previous tile has finished: claims follow actual progress, so a GPU
@@ -310,12 +321,91 @@ private:
             }
             auto t1 = std::chrono::high_resolution_clock::now();
             w->ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
-            if (config_.algorithmType != SchedulingAlgorithmType::DYNAMIC) renderTasks_[(size_t)w->index].time = (int)std::lround(w->ms);
+            if (config_.algorithmType != SchedulingAlgorithmType::DYNAMIC && config_.algorithmType != SchedulingAlgorithmType::LPT)
+                renderTasks_[(size_t)w->index].time = (int)std::lround(w->ms);
             {
                 std::lock_guard<std::mutex> lock(mu_);
                 if (--pending_ == 0) cvDone_.notify_all();
             }
         }
+    }
+
+    // ---- LPT: the multi-GPU schedule of the bench (sched.py: render_frame_lpt), in-process ---------------------------------------------
+    // A pixel is one sequential chain of spp samples, so a frame ends when its longest chain ends.  Every GPU traces a pilot pass over
+    // 1/N of the 8x4 blocks (rays per block), the slices meet in pinned host memory, ONE thread sorts the blocks by cost and deals them
+    // round-robin, every GPU renders its list most-expensive-first in one persistent launch and — if it is not the GPU that holds the
+    // frame's master copy — pushes its blocks there with peer stores on the same stream.  Replaces the reference's per-frame rectangles
+    // (src/RenderManager.h:264-408) for frames that are too short for feedback from the previous frame to help.
+    struct LptGpu {
+        uint32_t *dCosts = nullptr, *dBlocks = nullptr;
+        uint32_t capacity = 0;
+        std::vector<uint32_t> blocks;
+    };
+    void lptEnsure(int g, uint32_t n) {
+        LptGpu &s = lpt_[(size_t)g];
+        if (s.capacity >= n) return;
+        if (s.dCosts) cudaFree(s.dCosts);
+        if (s.dBlocks) cudaFree(s.dBlocks);
+        checkCudaErrors(cudaMalloc((void **)&s.dCosts, sizeof(uint32_t) * n));
+        checkCudaErrors(cudaMalloc((void **)&s.dBlocks, sizeof(uint32_t) * n));
+        s.capacity = n;
+    }
+    void lptRelease() {
+        for (size_t g = 0; g < lpt_.size(); g++) {
+            cudaSetDevice((int)g);
+            if (lpt_[g].dCosts) cudaFree(lpt_[g].dCosts);
+            if (lpt_[g].dBlocks) cudaFree(lpt_[g].dBlocks);
+        }
+        lpt_.clear();
+        if (lptHostCosts_) cudaFreeHost(lptHostCosts_);
+        lptHostCosts_ = nullptr;
+        lptHostCostsN_ = 0;
+    }
+    // all GPU-driving workers meet here; the last one to arrive runs `fn` before anyone leaves
+    template <class F>
+    void lptRendezvous(F fn) {
+        std::unique_lock<std::mutex> lock(lptMu_);
+        const uint64_t gen = lptGen_;
+        if (++lptArrived_ == (int)config_.gpuNumber) {
+            fn();
+            lptArrived_ = 0;
+            lptGen_++;
+            lptCv_.notify_all();
+        } else {
+            lptCv_.wait(lock, [&] { return lptGen_ != gen; });
+        }
+    }
+    void lptFrame(Worker *w, DevicePathTracer &dpt) {
+        const int g = w->device, N = (int)config_.gpuNumber;
+        const uint32_t W = config_.resolution.width, H = config_.resolution.height;
+        const uint32_t bw = (W + 7) / 8, bh = (H + 3) / 4, n = bw * bh;
+        cudaStream_t st = w->streams[0];
+        lptEnsure(g, n);
+        LptGpu &s = lpt_[(size_t)g];
+        dpt.syncCamera();
+        // 1. pilot pass over this GPU's slice of the block grid, slice -> pinned host
+        const uint32_t per = (n + (uint32_t)N - 1) / (uint32_t)N, first = std::min(n, (uint32_t)g * per), cnt = std::min(per, n - first);
+        checkPtcore(dpt.core(), ptcore_block_costs_range_async(dpt.core(), kLptPilotSpp, s.dCosts, first, cnt, st));
+        if (cnt) checkCudaErrors(cudaMemcpyAsync(lptHostCosts_ + first, s.dCosts + first, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, st));
+        checkCudaErrors(cudaStreamSynchronize(st));
+        // 2. one thread sorts (stable, descending) and deals the blocks
+        lptRendezvous([&] {
+            std::vector<uint32_t> order(n);
+            for (uint32_t i = 0; i < n; i++) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return lptHostCosts_[a] > lptHostCosts_[b]; });
+            for (int k = 0; k < N; k++) lpt_[(size_t)k].blocks.clear();
+            for (uint32_t i = 0; i < n; i++) lpt_[(size_t)(i % (uint32_t)N)].blocks.push_back((order[i] % bw) | ((order[i] / bw) << 16));
+        });
+        // 3. this GPU's list, most expensive first, one persistent launch; then its pixels travel to the master copy
+        const uint32_t mine = (uint32_t)s.blocks.size();
+        if (mine) {
+            checkCudaErrors(cudaMemcpyAsync(s.dBlocks, s.blocks.data(), sizeof(uint32_t) * mine, cudaMemcpyHostToDevice, st));
+            checkPtcore(dpt.core(), ptcore_render_blocks_async(dpt.core(), s.dBlocks, mine, st));
+            if (!dpt.rendersIntoMaster())
+                checkPtcore(dpt.core(), ptcore_gather_blocks_async(dpt.core(), framebuffer_->getDeviceRGBPtr(), framebuffer_->getDeviceYUVPtr(), s.dBlocks, mine, st));
+        }
+        dpt.synchronizeStream(st);
+        w->tiles = (int)mine;
     }
 
     // DSFL / DSDL: the arithmetic lives in TaskGenerator (pure functions of the previous frame's task times)
@@ -352,4 +442,12 @@ private:
     bool shutdown_ = false;
     std::atomic<int> nextTile_{0};
     FrameStats stats_;
+    static constexpr uint32_t kLptPilotSpp = 4;
+    std::vector<LptGpu> lpt_;
+    uint32_t *lptHostCosts_ = nullptr;
+    uint32_t lptHostCostsN_ = 0;
+    std::mutex lptMu_;
+    std::condition_variable lptCv_;
+    int lptArrived_ = 0;
+    uint64_t lptGen_ = 0;
 };

@@ -18,7 +18,9 @@ enum SchedulingAlgorithmType {
     FSFL,    // fixed size, fixed layout: equal cells, never changed
     DSFL,    // dynamic size, fixed layout: cell borders move towards equal render time
     DSDL,    // dynamic size, dynamic layout: time-weighted recursive bisection
-    DYNAMIC  // addition: small tiles pulled from one shared counter by every worker
+    DYNAMIC, // addition: small tiles pulled from one shared counter by every worker
+    LPT      // addition: pilot pass -> rays per 8x4 block -> blocks sorted by cost and dealt round-robin to the GPUs, each GPU takes its
+             // blocks most-expensive-first in ONE persistent launch; finished blocks go to the master frame with peer stores (NVLink)
 };
 
 struct RendererConfig {

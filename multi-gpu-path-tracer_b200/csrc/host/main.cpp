@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <iostream>
 #include <memory>
+#include <string>
 #include <thread>
 
 int main(int argc, char **argv) {
@@ -81,11 +82,22 @@ int main(int argc, char **argv) {
     }
     const RenderManager::FrameStats &fs = manager.lastFrameStats();
     double frameSamples = (double)config.resolution.width * config.resolution.height * config.samplesPerPixel;
+    std::string workerMs = "[", workerTiles = "[";
+    for (size_t i = 0; i < fs.worker_ms.size(); i++) {
+        char buf[64];
+        snprintf(buf, sizeof buf, "%s%.3f", i ? ", " : "", fs.worker_ms[i]);
+        workerMs += buf;
+        snprintf(buf, sizeof buf, "%s%d", i ? ", " : "", fs.worker_tiles[i]);
+        workerTiles += buf;
+    }
+    workerMs += "]";
+    workerTiles += "]";
     printf("CUDA_PROJECT_JSON {\"frame_ms\": %.3f, \"msamples_per_s\": %.3f, \"imbalance\": %.4f, \"gpus\": %u, \"streams_per_gpu\": %u, \"scheduler\": %d, "
-           "\"width\": %u, \"height\": %u, \"spp\": %u, \"depth\": %u, \"frames\": %u, \"total_samples\": %llu, \"total_rays\": %llu}\n",
+           "\"width\": %u, \"height\": %u, \"spp\": %u, \"depth\": %u, \"frames\": %u, \"total_samples\": %llu, \"total_rays\": %llu, "
+           "\"worker_ms\": %s, \"worker_tiles\": %s, \"peer_access_failures\": %d}\n",
            fs.frame_ms, frameSamples / (fs.frame_ms / 1e3) / 1e6, fs.imbalance, config.gpuNumber, config.streamsPerGpu, (int)config.algorithmType,
            config.resolution.width, config.resolution.height, config.samplesPerPixel, config.recursionDepth, config.framesToRender,
-           (unsigned long long)samples, (unsigned long long)rays);
+           (unsigned long long)samples, (unsigned long long)rays, workerMs.c_str(), workerTiles.c_str(), DevicePathTracer::peerAccessFailures().load());
     manager.reset();
     return 0;
 }

@@ -669,9 +669,22 @@ pto_vec3 pto_ray_color(const pto_world *w, pto_vec3 o, pto_vec3 d, uint32_t dept
 }
 
 /* Builder-defined mode with no counterpart in the reference (ptcore.h: PT_RNG_SAMPLE_KEYED): n_chunks > 0 keys the XORWOW stream by
- * (pixel, sample) — sample s of pixel p draws from curand_init(1984 + p + s * W * H, 0, 0) — and adds the samples chunk by chunk
+ * (pixel, sample) — sample s of pixel p draws from curand_init(splitmix64(1984 + p + s * W * H), 0, 0) — and adds the samples chunk by chunk
  * (ceil(spp / n_chunks) samples each), then the chunk sums in order, as the CUDA core does.  0 = the reference's streams (default). */
 static uint32_t g_keyed_chunks = 0;
+static int g_keyed_hash = 1;
+void pto_set_keyed_hash(int on) { g_keyed_hash = on; }
+/* seed of sample s of pixel p: the counter 1984 + p + s * W * H, passed through the splitmix64 finaliser so that the 64 bits XORWOW's
+ * curand_init(seed, 0, 0) derives its whole state from (curand_kernel.h:772-797) are well mixed even though consecutive counters differ
+ * in a few low bits only */
+uint64_t pto_keyed_seed(uint32_t pixel_index, uint32_t sample, uint32_t npix) {
+    uint64_t z = 1984ull + (uint64_t)pixel_index + (uint64_t)sample * (uint64_t)npix;
+    if (!g_keyed_hash) return z;
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
 void pto_set_keyed_chunks(uint32_t n_chunks) { g_keyed_chunks = n_chunks; }
 
 int pto_render(const pto_world *w, const PtCamera *cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t depth,
@@ -703,7 +716,7 @@ int pto_render(const pto_world *w, const PtCamera *cam, uint32_t width, uint32_t
                 const uint32_t chunk_spp = g_keyed_chunks ? (spp + g_keyed_chunks - 1) / g_keyed_chunks : 0;
                 v3 part = V(0, 0, 0);
                 for (uint32_t s = 0; s < spp; s++) {
-                    if (chunk_spp) pto_rng_init(&rs, 1984ull + (uint64_t)pixel_index + (uint64_t)s * (uint64_t)(width * height));
+                    if (chunk_spp) pto_rng_init(&rs, pto_keyed_seed((uint32_t)pixel_index, s, width * height));
                     float u = (float)(x + U(&c)) / (float)width;
                     float v = (float)(y + U(&c)) / (float)height;
                     v3 ro, rd;

@@ -39,7 +39,7 @@ def test_cli_single_gpu_equals_c_abi_and_reference_fixture(tmp_path, duck_file, 
     assert meta["gpus"] == 1 and meta["frames"] == 2 and meta["total_samples"] == 2 * 160 * 90 * 8
 
 
-@pytest.mark.parametrize("scheduler,streams", [("fsfl", 1), ("fsfl", 3), ("dsfl", 2), ("dsdl", 2), ("dynamic", 2)])
+@pytest.mark.parametrize("scheduler,streams", [("fsfl", 1), ("fsfl", 3), ("dsfl", 2), ("dsdl", 2), ("dynamic", 2), ("lpt", 1), ("lpt", 2)])
 def test_cli_schedulers_do_not_change_pixels(tmp_path, duck_file, scheduler, streams):
     if not CLI.exists():
         pytest.skip("cuda_project not built")
