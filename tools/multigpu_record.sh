@@ -21,7 +21,7 @@ done
 $CLI 0 $OUT/duck.ptscene --width 1920 --height 1080 --spp 1024 --depth 10 --gpus 1 --frames 2 --show-tasks 0 --out $OUT/cli_n1.ppm > $OUT/r02_cuda_project_n1.log 2>&1
 cmp $OUT/cli_n$N.ppm $OUT/cli_n1.ppm && echo "cuda_project: $N-GPU frame == 1-GPU frame" > $OUT/r02_cuda_project_cmp_n$N.txt
 rm -f $OUT/duck.ptscene $OUT/cli_n$N.ppm $OUT/cli_n1.ppm
-timeout 600 python -m pytest tests -x -q -m gpu -k "several_gpus or schedulers or keyed" > $OUT/r02_pytest_n$N.log 2>&1
+timeout 600 python -m pytest tests -x -q -m gpu -k "several_gpus or lpt" > $OUT/r02_pytest_n$N.log 2>&1
 tail -3 $OUT/r02_pytest_n$N.log
 for f in $OUT/r02_scale_n$N.json $OUT/r02_config5_n$N.json; do [ -s $f ] && python - "$f" <<'PY'
 import json, sys
