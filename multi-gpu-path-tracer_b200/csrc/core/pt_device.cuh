@@ -438,6 +438,13 @@ struct ShortStack {
     }
 };
 
+template <class STACK>
+__device__ __forceinline__ STACK make_stack(int32_t *local, uint32_t smem_col);
+template <>
+__device__ __forceinline__ LocalStack make_stack<LocalStack>(int32_t *local, uint32_t) { return LocalStack{local}; }
+template <>
+__device__ __forceinline__ ShortStack<8> make_stack<ShortStack<8>>(int32_t *local, uint32_t smem_col) { return ShortStack<8>{smem_col, local}; }
+
 __device__ __forceinline__ bool trav_leaf_held(const Trav &t) { return (t.leaf & 15) != 0; }
 template <class STACK>
 __device__ __forceinline__ void trav_push(Trav &t, const STACK &stack, int32_t x) { stack.put(t.sp++, x); }

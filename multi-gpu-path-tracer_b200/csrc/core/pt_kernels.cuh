@@ -17,6 +17,8 @@
 
 #include "pt_device.cuh"
 
+#include <type_traits>
+
 namespace ptc {
 
 constexpr int kBlockThreads = 128;
@@ -198,8 +200,16 @@ __global__ void __launch_bounds__(kBlockThreads) pt_persistent_kernel(const __gr
 // work item is then one CHUNK of a pixel's samples; its partial colour sum goes to accum[chunk][pixel] and pt_resolve_keyed_kernel
 // adds the chunks in order.  Same integrand, same estimator, different random numbers: parity with the reference is statistical
 // in this mode (converged RMSE), which is why it is never the default.
-template <bool SPHERES, bool RTOW, bool COUNT, int NODES, bool KEYED = false>  // NODES: 0 = 64-byte two-child nodes, 1 = four-wide nodes, 2 = 32-byte quantised two-child nodes, 3 = the same in shared memory
-__device__ __forceinline__ void wavefront_body(const RenderParams &p, const uint32_t smem_nodes) {
+// SSTACK: the first kWfStackK entries of every lane's traversal stack in shared memory (ShortStack, pt_device.cuh) instead of local
+// memory.  Local memory (stack + spills) is the largest consumer of L1 sectors in the capture of the shipped kernel (100 G of 152 G per
+// 1024-spp frame, profiles/r02_ncu_wavefront_1080p_1024spp.txt), so this looked like the next step after the shared-memory nodes —
+// measured on B200 it LOSES 12 % (2837 -> 2491 Msamples/s at 128 spp, 2869 -> 2524 at 1024 spp; same pixels): 32 KB more shared memory
+// move the carve-out from 100 to 132 KB and the predicated LDS / STS plus the overflow branch cost more than the L1-resident LDL / STL they
+// replace.  Compiled out (kWfSmemStack = false); the pool kernel uses the same ShortStack.
+constexpr int kWfStackK = 8;
+constexpr bool kWfSmemStack = false;
+template <bool SPHERES, bool RTOW, bool COUNT, int NODES, bool KEYED = false, bool SSTACK = false>  // NODES: 0 = 64-byte two-child nodes, 1 = four-wide nodes, 2 = 32-byte quantised two-child nodes, 3 = the same in shared memory
+__device__ __forceinline__ void wavefront_body(const RenderParams &p, const uint32_t smem_nodes, const uint32_t smem_stack = 0) {
     constexpr bool WIDE = NODES == 1, QUANT = NODES >= 2, SMEM = NODES == 3;
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t total_items = KEYED ? work_total(p) * p.keyed_my_chunks : work_total(p);
@@ -217,8 +227,9 @@ __device__ __forceinline__ void wavefront_body(const RenderParams &p, const uint
     float3 col = f3(0.f, 0.f, 0.f), att = f3(1.f, 1.f, 1.f), ro = f3(0.f, 0.f, 0.f), rd = f3(0.f, 0.f, 1.f);
     uint32_t n_rays = 0, n_box = 0, n_tri = 0, n_light = 0, pixel_rays = 0;
     unsigned long long acc_box = 0, acc_tri = 0, acc_light = 0;
-    int32_t stack_mem[kStackSize];
-    const LocalStack stack{stack_mem};
+    int32_t stack_mem[SSTACK ? kStackSize - kWfStackK : kStackSize];
+    typedef typename std::conditional<SSTACK, ShortStack<kWfStackK>, LocalStack>::type StackT;
+    const StackT stack = make_stack<StackT>(stack_mem, smem_stack + lane * 4u);
     Trav tr;
     if (QUANT) trav_begin_grid(tr, stack, p.scene, ro, rd);
     else trav_begin(tr, stack, ro, rd);
@@ -304,13 +315,13 @@ __device__ __forceinline__ void wavefront_body(const RenderParams &p, const uint
             if (n_active == 0 || n_paths - n_active >= wait_for) break;
             if (__popc(m_node) >= __popc(m_prim)) {
                 if (!WIDE && node_burst == 2) {  // the default, without the loop bookkeeping
-                    if (can_node) trav_node_step<COUNT, QUANT, LocalStack, SMEM>(p.scene, tr, stack, 0.001f, n_box, smem_nodes);
-                    if (tr.cur >= 0) trav_node_step<COUNT, QUANT, LocalStack, SMEM>(p.scene, tr, stack, 0.001f, n_box, smem_nodes);
+                    if (can_node) trav_node_step<COUNT, QUANT, StackT, SMEM>(p.scene, tr, stack, 0.001f, n_box, smem_nodes);
+                    if (tr.cur >= 0) trav_node_step<COUNT, QUANT, StackT, SMEM>(p.scene, tr, stack, 0.001f, n_box, smem_nodes);
                 } else {
                     for (int k = 0; k < node_burst; k++)
                         if (tr.cur >= 0) {
                             if (WIDE) trav_node_step4<COUNT>(p.scene, tr, stack, 0.001f, n_box);
-                            else trav_node_step<COUNT, QUANT, LocalStack, SMEM>(p.scene, tr, stack, 0.001f, n_box, smem_nodes);
+                            else trav_node_step<COUNT, QUANT, StackT, SMEM>(p.scene, tr, stack, 0.001f, n_box, smem_nodes);
                         }
                 }
             } else {
@@ -375,10 +386,12 @@ __global__ void __launch_bounds__(kBlockThreads, 8) pt_wavefront_kernel(const __
 constexpr int kSmemKernelThreads = 1024;
 template <bool SPHERES, bool RTOW, bool COUNT, bool KEYED = false>
 __global__ void __launch_bounds__(kSmemKernelThreads, 1) pt_wavefront_smem_kernel(const __grid_constant__ RenderParams p, const int32_t n_nodes) {
-    extern __shared__ uint4 smem_nodesq[];
+    extern __shared__ uint4 smem_nodesq[];  // [2 * n_nodes] quantised nodes, then [32 warps][kWfStackK][32 lanes] stack words
     for (int i = (int)threadIdx.x; i < n_nodes * 2; i += kSmemKernelThreads) smem_nodesq[i] = __ldg(&p.scene.nodesq[i]);
     __syncthreads();
-    wavefront_body<SPHERES, RTOW, COUNT, 3, KEYED>(p, (uint32_t)__cvta_generic_to_shared(smem_nodesq));
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_nodesq);
+    const uint32_t stacks = base + (uint32_t)n_nodes * 32u + (threadIdx.x >> 5) * (uint32_t)(kWfStackK * 128);
+    wavefront_body<SPHERES, RTOW, COUNT, 3, KEYED, kWfSmemStack>(p, base, stacks);
 }
 
 // PT_RNG_SAMPLE_KEYED: adds the chunk sums of every pixel in chunk order and stores the pixel (quantiser + RGB8 + I420 as always)

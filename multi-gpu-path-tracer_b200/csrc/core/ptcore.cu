@@ -237,7 +237,7 @@ cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaS
     if (h->kernel == PT_KERNEL_POOL && h->bvh_width != 4 && rp.depth > 0) return launch_pool<S, R, C>(h, rp, stream);
     if (!direct && h->kernel == PT_KERNEL_PERSISTENT && h->smem_nodes && h->bvh_width != 4 && use_quantised(h) &&
         (size_t)h->blob.n_nodes * 32 <= (size_t)h->smem_nodes_max_bytes) {
-        const size_t bytes = (size_t)h->blob.n_nodes * 32;
+        const size_t bytes = (size_t)h->blob.n_nodes * 32 + (kWfSmemStack ? (size_t)(kSmemKernelThreads / 32) * kWfStackK * 128 : 0);  // nodes (+ the warps' short stacks)
         cudaError_t e = cudaFuncSetAttribute(pt_wavefront_smem_kernel<S, R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
         uint32_t grid = (uint32_t)h->sm_count;
@@ -278,7 +278,7 @@ cudaError_t launch_keyed_variant(ptcore *h, const RenderParams &rp, cudaStream_t
     const uint32_t total = rp.tiles.first_item[rp.tiles.n] * rp.keyed_my_chunks;
     if (total == 0) return cudaSuccess;
     if (h->smem_nodes && use_quantised(h) && (size_t)h->blob.n_nodes * 32 <= (size_t)h->smem_nodes_max_bytes) {
-        const size_t bytes = (size_t)h->blob.n_nodes * 32;
+        const size_t bytes = (size_t)h->blob.n_nodes * 32 + (kWfSmemStack ? (size_t)(kSmemKernelThreads / 32) * kWfStackK * 128 : 0);
         cudaError_t e = cudaFuncSetAttribute(pt_wavefront_smem_kernel<S, R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
         uint32_t grid = (uint32_t)h->sm_count;
