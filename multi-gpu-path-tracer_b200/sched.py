@@ -55,8 +55,9 @@ class RankRenderer:
         self.device = device
         self.width, self.height = width, height
         n_rgb, n_yuv = width * height * 3, width * height * 3 // 2
-        self.fb = torch.zeros(n_rgb + n_yuv, dtype=torch.uint8, device=device)
-        self.rgb, self.yuv = self.fb[:n_rgb], self.fb[n_rgb:]
+        self.fb = torch.zeros((n_rgb + n_yuv + 15) // 16 * 16, dtype=torch.uint8, device=device)
+        self.rgb, self.yuv = self.fb[:n_rgb], self.fb[n_rgb:n_rgb + n_yuv]
+        self.fb_words = self.fb.view(torch.int32)  # what travels: see _gather
         self.streams = [torch.cuda.Stream(device=device) for _ in range(n_streams)]
         pt.bind_framebuffer(self.rgb.data_ptr(), self.yuv.data_ptr(), width, height)
         self.launches = 0
@@ -91,7 +92,9 @@ class RankRenderer:
 
     def _gather(self) -> None:
         import torch.distributed as dist
-        dist.reduce(self.fb, dst=0, op=dist.ReduceOp.SUM)  # claimed pixel sets are disjoint, the rest is zero: a uint8 SUM is the gather
+        # claimed pixel sets are disjoint and the rest is zero, so a SUM is the gather; summed as 32-bit words (every byte is non-zero on
+        # at most one rank: no carries), which NCCL reduces several times faster than 8-bit elements (15.6 -> ms at 8 ranks, r02_scale_n8)
+        dist.reduce(self.fb_words, dst=0, op=dist.ReduceOp.SUM)
 
     def reset_stage_times(self) -> None:
         self.stage_events = []
