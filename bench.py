@@ -50,9 +50,9 @@ def ncu_counters(kernel: str):
         f = ln.split()
         if ln.startswith("== ") and out:
             break  # first kernel of the file only
-        if len(f) == 3 and f[1] in scale:
+        if len(f) == 3:
             try:
-                out[f[0]] = float(f[2]) * scale[f[1]]
+                out[f[0]] = float(f[2]) * scale.get(f[1], 1.0)
             except ValueError:
                 pass
         elif len(f) == 2:
@@ -489,12 +489,16 @@ def main():
             if inst:
                 cand["issue"] = {"bound": "issue", "achieved": inst / kernel_s / 1e9, "peak": issue_peak, "unit": "G warp-instructions/s", "frac": inst / kernel_s / 1e9 / issue_peak,
                                  "warp_instructions_per_launch": inst, "threads_per_instruction": tpi, "useful_lane_issue_frac": (inst / kernel_s / 1e9 / issue_peak) * (tpi / 32.0) if tpi else None}
-            if nc.get("l1tex__t_bytes.sum"):
-                l1_peak = 148 * 128 * sm_mhz * 1e6 / 1e9
-                cand["l1"] = {"bound": "l1", "achieved": nc["l1tex__t_bytes.sum"] / kernel_s / 1e9, "peak": l1_peak, "unit": "GB/s", "frac": nc["l1tex__t_bytes.sum"] / kernel_s / 1e9 / l1_peak}
-            if nc.get("lts__t_bytes.sum"):
-                l2_peak = 6300 * sm_mhz * 1e6 / 1e9
-                cand["l2"] = {"bound": "l2", "achieved": nc["lts__t_bytes.sum"] / kernel_s / 1e9, "peak": l2_peak, "unit": "GB/s", "frac": nc["lts__t_bytes.sum"] / kernel_s / 1e9 / l2_peak}
+            # L1 / L2: ncu's own fraction of the unit's peak during the captured launch, rescaled to the duration measured live
+            t_ncu = nc.get("gpu__time_duration.sum", 0.0) / 1e3  # the summary stores ms
+            scale = (t_ncu / kernel_s) if t_ncu > 0 else 1.0
+            if nc.get("l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"):
+                f = nc["l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"] / 100.0 * scale
+                cand["l1"] = {"bound": "l1", "achieved": f * 100.0, "peak": 100.0, "unit": "% of the L1 LSU data pipe's wavefront rate", "frac": f}
+            if nc.get("lts__throughput.avg.pct_of_peak_sustained_elapsed"):
+                f = nc["lts__throughput.avg.pct_of_peak_sustained_elapsed"] / 100.0 * scale
+                cand["l2"] = {"bound": "l2", "achieved": f * 100.0, "peak": 100.0, "unit": "% of L2 (lts) throughput", "frac": f,
+                              "bytes_per_launch": nc.get("lts__t_sectors.sum", 0.0) * 32.0}
             if traffic:
                 cand["hbm"] = {"bound": "hbm", "achieved": traffic / kernel_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": traffic / kernel_s / 1e9 / peaks["hbm_gbs"],
                                "note": "real DRAM bytes of the launch (ncu), not algorithmic bytes: the 5 MB scene is cache-resident"}

@@ -11,7 +11,10 @@ KEYS = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum', 'l1tex__t_bytes.sum',
         'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'smsp__warps_eligible.avg.per_cycle_active', 'smsp__sass_inst_executed_op_local_ld.sum',
         'smsp__sass_inst_executed_op_local_st.sum', 'smsp__inst_executed_op_branch.sum', 'sm__cycles_elapsed.avg', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
-        'lts__t_bytes.sum.per_second', 'l1tex__t_bytes.sum.per_second', 'sm__inst_executed.avg.per_cycle_elapsed']
+        'lts__t_bytes.sum.per_second', 'l1tex__t_bytes.sum.per_second', 'sm__inst_executed.avg.per_cycle_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_sectors.sum', 'launch__shared_mem_config_size', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum',
+        'l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct', 'l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct']
 
 
 def page(rep, name):
