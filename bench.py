@@ -8,7 +8,10 @@ models/cornell_duck.glb, 1920x1080, 1024 spp, max depth 10, the reference's defa
 A "step" is one whole frame (W*H*spp camera paths).  `value` is whole-job throughput with the compiled
 scene resident in HBM; `e2e` is the same frame through the C ABI with HOST buffers (scene blob H2D from
 pinned memory + camera + render + RGB/I420 D2H inside the timed region).  N > 1 splits the SAME frame
-over the ranks (strong scaling): dynamic tile claims from a node-wide counter, one NCCL reduce at frame end.
+over the ranks (strong scaling): a pilot pass (1/N of the blocks per rank, one small all-reduce) measures rays per 8x4 block, the
+blocks are sorted by cost and dealt round-robin (LPT), one NCCL reduce gathers the frame (`--sched tiles`: dynamic tile claims).
+Beside `value` the line carries `stages_ms`, `warp_retire`, `rng_keyed` (the (pixel, sample)-keyed RNG mode, statistical parity
+only) and `ref_gpu` (the reference's own CUDA renderer with gpuNumber = N on the same box).
 """
 from __future__ import annotations
 

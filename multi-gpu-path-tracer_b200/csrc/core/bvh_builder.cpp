@@ -12,6 +12,8 @@
 #include <thread>
 
 namespace ptc {
+
+static inline float inf_f() { return std::numeric_limits<float>::infinity(); }
 namespace {
 
 struct Box {
@@ -280,21 +282,24 @@ BvhBuildResult build_bvh(const std::vector<PrimBounds> &bounds, const BvhBuildOp
     BvhBuildResult out;
     const float inf = std::numeric_limits<float>::infinity();
     auto emptyChild = [&](FlatNode &n, int side) {
+        // all six planes at +inf, and (below) a leaf reference of ZERO primitives: a (+inf, -inf) box is ACCEPTED by a min / max slab test
+        //  and even this one is while nothing has been hit yet (far = FLT_MAX * slack = +inf), so what makes an absent child
+        // harmless is its empty leaf, not its box
         n.bx[side * 2] = n.by[side * 2] = n.bz[side * 2] = inf;
-        n.bx[side * 2 + 1] = n.by[side * 2 + 1] = n.bz[side * 2 + 1] = -inf;
+        n.bx[side * 2 + 1] = n.by[side * 2 + 1] = n.bz[side * 2 + 1] = inf;
     };
     if (bounds.empty()) {
         FlatNode n{};
         emptyChild(n, 0);
         emptyChild(n, 1);
-        n.left = n.right = leaf_ref(0, 1);  // never entered
+        n.left = n.right = leaf_ref(0, 0);  // a leaf of ZERO primitives: whatever the slab test says, the walk tests nothing (a zero cursor is never 'held')
         out.nodes.push_back(n);
         out.depth = 1;
         FlatNode4 n4{};
         for (int c = 0; c < 4; c++) {
             n4.lox[c] = n4.loy[c] = n4.loz[c] = inf;
-            n4.hix[c] = n4.hiy[c] = n4.hiz[c] = -inf;
-            n4.ref[c] = leaf_ref(0, 1);
+            n4.hix[c] = n4.hiy[c] = n4.hiz[c] = inf;
+            n4.ref[c] = leaf_ref(0, 0);
         }
         out.nodes4.push_back(n4);
         out.depth4 = 1;
@@ -320,7 +325,7 @@ BvhBuildResult build_bvh(const std::vector<PrimBounds> &bounds, const BvhBuildOp
         n.bz[0] = t.box.lo[2]; n.bz[1] = t.box.hi[2];
         emptyChild(n, 1);
         n.left = leaf_ref(t.first, cnt);
-        n.right = leaf_ref(0, 1);
+        n.right = leaf_ref(0, 0);  // absent child: a leaf of zero primitives
         out.nodes.push_back(n);
         out.n_leaves = 1;
         out.sah_cost = opt.intersect_cost * (double)t.count;
@@ -366,8 +371,8 @@ BvhBuildResult build_bvh(const std::vector<PrimBounds> &bounds, const BvhBuildOp
     {
         auto emptySlot = [&](FlatNode4 &n, int c) {
             n.lox[c] = n.loy[c] = n.loz[c] = inf;
-            n.hix[c] = n.hiy[c] = n.hiz[c] = -inf;
-            n.ref[c] = leaf_ref(0, 1);
+            n.hix[c] = n.hiy[c] = n.hiz[c] = inf;
+            n.ref[c] = leaf_ref(0, 0);
         };
         auto setSlot = [&](FlatNode4 &n, int c, const Box &bx, int32_t ref) {
             n.lox[c] = bx.lo[0]; n.hix[c] = bx.hi[0];
@@ -437,7 +442,7 @@ QuantGrid quantise_nodes(const std::vector<FlatNode> &nodes, std::vector<QuantNo
     for (const FlatNode &n : nodes)
         for (int side = 0; side < 2; side++) {
             const float b[3][2] = {{n.bx[side * 2], n.bx[side * 2 + 1]}, {n.by[side * 2], n.by[side * 2 + 1]}, {n.bz[side * 2], n.bz[side * 2 + 1]}};
-            if (!(b[0][0] <= b[0][1])) continue;  // absent child
+            if (!(b[0][0] < inf_f())) continue;  // absent child (all planes at +inf)
             for (int k = 0; k < 3; k++) {
                 if (std::isfinite(b[k][0])) lo[k] = std::min(lo[k], (double)b[k][0]);
                 if (std::isfinite(b[k][1])) hi[k] = std::max(hi[k], (double)b[k][1]);
@@ -469,7 +474,7 @@ QuantGrid quantise_nodes(const std::vector<FlatNode> &nodes, std::vector<QuantNo
         const FlatNode &n = nodes[i];
         QuantNode &q = out[i];
         auto pack = [&](const float *b, int side, int k) -> uint32_t {
-            if (!(b[side * 2] <= b[side * 2 + 1])) return 0x0000u | (32767u);  // absent child: min 32767, max 0 (the duplicate leaf it points to is harmless)
+            if (!(b[side * 2] < inf_f())) return 0x0000u | (32767u);  // absent child: min 32767, max 0 — near > far for every ray
             return plane(b[side * 2], k, false) | (plane(b[side * 2 + 1], k, true) << 16);
         };
         q.lx = pack(n.bx, 0, 0); q.rx = pack(n.bx, 1, 0);
@@ -490,7 +495,7 @@ const char *validate_quantised(const std::vector<FlatNode> &nodes, const std::ve
         const float *fb[3] = {n.bx, n.by, n.bz};
         const uint32_t qb[3][2] = {{q[i].lx, q[i].rx}, {q[i].ly, q[i].ry}, {q[i].lz, q[i].rz}};
         for (int side = 0; side < 2; side++) {
-            if (!(n.bx[side * 2] <= n.bx[side * 2 + 1])) continue;  // absent child
+            if (!(n.bx[side * 2] < inf_f())) continue;  // absent child
             double eq[3], ef[3];
             for (int k = 0; k < 3; k++) {
                 const float lo = fb[k][side * 2], hi = fb[k][side * 2 + 1];
@@ -798,7 +803,7 @@ const char *validate_bvh(const BvhBuildResult &bvh, const std::vector<PrimBounds
         for (int s = 0; s < 2; s++) {
             float lo[3] = {nd.bx[s * 2], nd.by[s * 2], nd.bz[s * 2]}, hi[3] = {nd.bx[s * 2 + 1], nd.by[s * 2 + 1], nd.bz[s * 2 + 1]};
             int32_t ref = s ? nd.right : nd.left;
-            if (lo[0] > hi[0]) continue;  // absent child
+            if (!(lo[0] < inf_f())) continue;  // absent child
             for (int k = 0; k < 3; k++)
                 if (lo[k] < w.lo[k] || hi[k] > w.hi[k]) return "child box not inside parent box";
             if (ref >= 0) {
@@ -843,7 +848,7 @@ const char *validate_bvh4(const BvhBuildResult &bvh, const std::vector<PrimBound
         const FlatNode4 &nd = bvh.nodes4[(size_t)w.node];
         for (int c = 0; c < 4; c++) {
             float lo[3] = {nd.lox[c], nd.loy[c], nd.loz[c]}, hi[3] = {nd.hix[c], nd.hiy[c], nd.hiz[c]};
-            if (lo[0] > hi[0]) continue;  // unused slot
+            if (!(lo[0] < inf_f())) continue;  // unused slot
             for (int k = 0; k < 3; k++)
                 if (lo[k] < w.lo[k] || hi[k] > w.hi[k]) return "wide child box not inside parent box";
             int32_t ref = nd.ref[c];

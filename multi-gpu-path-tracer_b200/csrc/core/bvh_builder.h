@@ -22,7 +22,7 @@ namespace ptc {
 //   q[2] = (l.min.z, l.max.z, r.min.z, r.max.z)
 //   q[3] = (left ref, right ref, unused, unused) as int32
 // child ref >= 0: index of an inner node; ref < 0: leaf, ~ref = (first_prim << 4) | count, 1 <= count <= 8.
-// An absent child (single-leaf scenes) has an inverted box (+inf, -inf) that no ray enters.
+// An absent child (single-leaf scenes) has all six planes at +inf and refers to a leaf of ZERO primitives: entering it tests nothing.
 struct alignas(64) FlatNode {
     float bx[4];
     float by[4];
@@ -52,7 +52,7 @@ struct QuantGrid {
 // 128 bytes = eight 16-byte quads; the kernel fetches the first seven.
 //   q[0] = lo.x of children 0..3, q[1] = hi.x, q[2] = lo.y, q[3] = hi.y, q[4] = lo.z, q[5] = hi.z, q[6] = child refs (int32)
 // Built by collapsing the SAH BVH2: a node's inner children are opened (largest surface area first) until it has four
-// children or only leaves.  Unused slots carry an inverted box and are never entered.
+// children or only leaves.  Unused slots have all planes at +inf and refer to a leaf of zero primitives.
 struct alignas(128) FlatNode4 {
     float lox[4], hix[4], loy[4], hiy[4], loz[4], hiz[4];
     int32_t ref[4];

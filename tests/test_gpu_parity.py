@@ -558,3 +558,19 @@ def test_keyed_rng_mode_converges_to_the_reference_renderer(tracer, duck, ptb):
                  within_3se=float((np.abs(d) <= 3 * np.sqrt(2) * np.minimum(se, 255.0) + 1.5).mean()), median_abs=float(np.median(np.abs(d))))
     print(stats)
     assert abs(stats["mean_diff"]) <= 0.15 and stats["rmse_4x4"] <= 2.0 and stats["within_3se"] >= 0.97, stats
+
+
+def test_absent_child_of_a_single_leaf_scene_is_never_tested(tracer, ptb, oracle):
+    """the root of a one-leaf scene has an absent second child.  It refers to a leaf of zero primitives, so no ray tests
+    primitive 0 twice (and an empty scene tests nothing at all)."""
+    sc = ptb.Scene(tri_pos=np.array([[-1, -1, -3, 1, -1, -3, 0, 1, -3]], np.float32), tri_uv=np.zeros((1, 6), np.float32), tri_mat=np.zeros(1, np.int32),
+                   mats=np.array([(ptb.PT_MAT_UNIVERSAL, (0.5, 0.5, 0.5), (1, 1, 1), -1, -1, 0, 1.5)], ptb.MAT_DTYPE))
+    tracer.set_option(ptb.PT_OPT_COUNT_TESTS, 1)
+    for kernel in (ptb.PT_KERNEL_PERSISTENT, ptb.PT_KERNEL_POOL, ptb.PT_KERNEL_DIRECT):
+        tracer.reset_stats()
+        rgb, _ = render(tracer, sc, 64, 36, 2, 4, kernel=kernel, ptb=ptb)
+        st = tracer.stats()
+        assert st["rays"] > 0 and st["tri_tests"] <= st["rays"], (kernel, st["tri_tests"], st["rays"])
+        ref, _, _ = oracle.render(sc, 64, 36, 2, 4)
+        assert np.array_equal(rgb, ref)  # an emitter seen directly: no rounding-sensitive bounce
+    tracer.set_option(ptb.PT_OPT_KERNEL, ptb.PT_KERNEL_PERSISTENT)
