@@ -20,7 +20,7 @@ using namespace ptc;
 
 namespace {
 
-constexpr int kCounterRing = 1024;
+constexpr int kCounterRing = 8192;  // one work counter per launch in flight; a launch reuses a slot only after 8192 later launches were issued on this handle
 
 thread_local std::string g_create_error;
 

@@ -57,10 +57,12 @@ public:
         {
             // the reference passes CameraConfig by value at every launch (:210), so a camera edited by
             // another thread takes effect at the next task; mirror that with a compare-and-upload
+            // the launch snapshots the core's camera (by value into the kernel's parameters): keep the lock until it is issued, so that
+            // a worker of another stream cannot re-upload the camera between this check and this launch
             std::lock_guard<std::mutex> lock(mu_);
             if (!sameCamera(cameraConfig_, uploadedCamera_)) uploadCamera();
+            checkPtcore(core_, ptcore_render_tile_async(core_, task.offset_x, task.offset_y, task.width, task.height, stream));
         }
-        checkPtcore(core_, ptcore_render_tile_async(core_, task.offset_x, task.offset_y, task.width, task.height, stream));
         if (!rendersIntoMaster_) gatherTile(task, stream);
     }
 
