@@ -77,6 +77,8 @@ struct ptcore {
     int node_format = PT_NODES_AUTO;
     int sah_isect_x100 = 120;
     int lanes_per_warp = 32;
+    bool l2_persist_nodes = false, l2_limits_known = false;
+    size_t l2_max_persist = 0, l2_max_window = 0, l2_set_aside = 0;
     int rng_mode = PT_RNG_STREAM;
     int rng_chunks = 16;
     bool sticky_textures = true;
@@ -307,7 +309,40 @@ cudaError_t launch_keyed(ptcore *h, const RenderParams &rp, cudaStream_t stream)
     return launch_keyed_variant<true, true>(h, rp, stream);
 }
 
+// PT_OPT_L2_PERSIST_NODES: scenes whose compiled data exceed L2 (the 2 M-triangle mesh: 396 MB) walk the tree at DRAM latency.  The
+// quantised node array (36 MB there) is what 13 of a ray's 15 dependent loads touch: mark it persisting in L2 for the launches of this
+// stream (access-policy window), so that the triangles, frames and texels that stream through L2 cannot evict it.
+void apply_l2_policy(ptcore *h, cudaStream_t stream) {
+    if (!h->l2_persist_nodes || !h->have_scene) return;
+    if (!h->l2_limits_known) {
+        int maxPersist = 0, maxWindow = 0;
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+        cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+        h->l2_max_persist = (size_t)std::max(0, maxPersist);
+        h->l2_max_window = (size_t)std::max(0, maxWindow);
+        h->l2_limits_known = true;
+    }
+    const bool quant = use_quantised(h);
+    const uint8_t *base = h->blob.dev + (quant ? h->blob.off_nodesq : h->blob.off_nodes);
+    size_t bytes = (size_t)h->blob.n_nodes * (quant ? 32 : 64);
+    if (h->l2_max_persist == 0 || h->l2_max_window == 0 || bytes == 0) return;
+    if (h->l2_set_aside != std::min(bytes, h->l2_max_persist)) {
+        h->l2_set_aside = std::min(bytes, h->l2_max_persist);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_set_aside);
+    }
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    attr.accessPolicyWindow.base_ptr = const_cast<uint8_t *>(base);
+    attr.accessPolicyWindow.num_bytes = std::min(bytes, h->l2_max_window);
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)h->l2_set_aside / (double)attr.accessPolicyWindow.num_bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(stream ? stream : cudaStreamLegacy, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
+}
+
 cudaError_t launch(ptcore *h, const RenderParams &rp, cudaStream_t stream) {
+    apply_l2_policy(h, stream);
     if ((h->kernel == PT_KERNEL_PERSISTENT || h->kernel == PT_KERNEL_POOL) && h->bvh_width == 4 && !h->blob.has_nodes4) return cudaErrorNotSupported;  // upload the scene with PT_OPT_BVH_WIDTH = 4 first
     const bool direct = h->kernel == PT_KERNEL_DIRECT;
     const bool S = h->blob.has_spheres, R = h->blob.has_rtow, C = h->count_tests;
@@ -851,6 +886,7 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
             h->lanes_per_warp = (int)value;
             return PT_OK;
         case PT_OPT_STICKY_TEXTURES: h->sticky_textures = value != 0; return PT_OK;
+        case PT_OPT_L2_PERSIST_NODES: h->l2_persist_nodes = value != 0; return PT_OK;
         case PT_OPT_RNG_MODE:
             if (value != PT_RNG_STREAM && value != PT_RNG_SAMPLE_KEYED) return fail(h, PT_ERR_INVALID_ARGUMENT, "unknown rng mode");
             h->rng_mode = (int)value;

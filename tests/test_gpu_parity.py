@@ -574,3 +574,23 @@ def test_absent_child_of_a_single_leaf_scene_is_never_tested(tracer, ptb, oracle
         ref, _, _ = oracle.render(sc, 64, 36, 2, 4)
         assert np.array_equal(rgb, ref)  # an emitter seen directly: no rounding-sensitive bounce
     tracer.set_option(ptb.PT_OPT_KERNEL, ptb.PT_KERNEL_PERSISTENT)
+
+
+def test_config3_materials_agree_with_the_kernel_assembled_from_the_references_dead_classes(tracer, ptb, tmp_path):
+    """SURVEY 8a D1-D6 have no reference renderer; oracle/_ref/ref_gpu_spheres is the closest thing: the reference's own sphere /
+    lambertian / metal / dielectric / diffuse_light classes (dead code there) under a per-pixel kernel with the reference's RNG seeding
+    and camera.  Same streams, same glue, so the images agree like two builds of the same program (gate-B style tolerance; glass and
+    metal paths are chaotic, hence the wider rate)."""
+    exe = ROOT / "oracle" / "_ref" / "ref_gpu_spheres"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/ref_gpu_spheres did not travel to this box")
+    sc, cam = ptb.scenes.rtow_sphere_field()
+    w, h, spp, depth = 160, 90, 8, 10
+    flat, ppm = tmp_path / "s.ptscene", tmp_path / "ref.ppm"
+    flat.write_bytes(sc.to_ptscene_bytes())
+    r = subprocess.run([str(exe), str(flat), str(w), str(h), str(spp), str(depth), str(ppm), "--cam", *map(str, (*cam["look_from"], *cam["front"], cam["vfov"], cam["hfov"]))],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "REF_GPU_JSON" in r.stdout, (r.stdout + r.stderr)[-400:]
+    ref = np.array(Image.open(ppm).convert("RGB"))
+    rgb, _ = render(tracer, sc, w, h, spp, depth, cam)
+    print(check(rgb, ref, spp, rate=6e-3))

@@ -15,7 +15,8 @@ scene = ptb200.scenes.displaced_sphere_in_cornell(duck, n=n)
 w, h = 3840, 2160
 fb = torch.zeros(w * h * 3, dtype=torch.uint8, device="cuda")
 ref = None
-for name, opts in (("bvh2 wavefront", {}), ("bvh4 wavefront", {ptb200.PT_OPT_BVH_WIDTH: 4}), ("bvh2 pool", {ptb200.PT_OPT_KERNEL: ptb200.PT_KERNEL_POOL}),
+for name, opts in (("bvh2 wavefront", {}), ("bvh2 wavefront + nodes persisting in L2", {ptb200.PT_OPT_L2_PERSIST_NODES: 1}), ("bvh4 wavefront", {ptb200.PT_OPT_BVH_WIDTH: 4}),
+                   ("bvh2 pool", {ptb200.PT_OPT_KERNEL: ptb200.PT_KERNEL_POOL}), ("bvh2 pool + nodes persisting in L2", {ptb200.PT_OPT_KERNEL: ptb200.PT_KERNEL_POOL, ptb200.PT_OPT_L2_PERSIST_NODES: 1}),
                    ("bvh2 wavefront float nodes", {ptb200.PT_OPT_NODE_FORMAT: ptb200.PT_NODES_FULL})):
     pt = ptb200.PathTracer(0)
     for k, v in opts.items():
