@@ -15,6 +15,7 @@
 // Parity for this stage is pinned by SURVEY.md Appendix A (counts, bounds,
 // first/last triangles), not by the reference (it has no tests): "parity unpinned".
 #include "HostScene.h"
+#include "JpegDecoder.h"
 
 #include <zlib.h>
 
@@ -343,13 +344,31 @@ HostTexture texture_from_bytes(const unsigned char *bytes, size_t n, const std::
     std::vector<unsigned char> px;
     std::string err;
     static const unsigned char png_sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
-    if (n < 8 || memcmp(bytes, png_sig, 8) != 0) {
-        // The reference decodes textures with stb_image (src/HostScene.cpp:10-51), which also reads JPEG / BMP / TGA / GIF / PSD / HDR; only
-        // the PNG decoder is restated here.  Such an image does not abort the load: the material keeps its slot and gets a texture
-        // without texels, which the device shades with the reference's own placeholder colour for a texture without data
+    const bool is_jpeg = n >= 3 && bytes[0] == 0xFF && bytes[1] == 0xD8 && bytes[2] == 0xFF;
+    if (is_jpeg) {
+        // baseline / extended-sequential JPEG: JpegDecoder.h restates the three implementation-defined steps of stb_image (IDCT, chroma
+        // upsampling, YCbCr -> RGB), so the texels are the reference's byte for byte (pinned against stb_image itself: oracle/ref_stb.c)
+        ptjpeg::Decoder dec;
+        if (dec.decode(bytes, n, w, h, ch, px, err)) {
+            HostTexture t;
+            t.width = w;
+            t.height = h;
+            t.data.resize((size_t)w * (size_t)h);
+            // three channels as decoded; a grey JPEG is replicated, which is what stbi_load(path, ..., 3) of the reference's file path does
+            // (its embedded-texture path walks a 1-channel buffer three bytes at a time: out of bounds there, src/HostScene.cpp:18-26,37-46)
+            for (size_t j = 0; j < t.data.size(); j++)
+                t.data[j] = ch == 3 ? make_float3((float)px[3 * j], (float)px[3 * j + 1], (float)px[3 * j + 2]) : make_float3((float)px[j], (float)px[j], (float)px[j]);
+            return t;
+        }
+        fprintf(stderr, "SceneLoader: JPEG texture %s: %s\n", what.c_str(), err.c_str());
+    }
+    if (is_jpeg || n < 8 || memcmp(bytes, png_sig, 8) != 0) {
+        // The reference decodes textures with stb_image (src/HostScene.cpp:10-51), which also reads progressive JPEG / BMP / TGA / GIF / PSD /
+        // HDR; PNG and sequential JPEG are restated here.  Any other image does not abort the load: the material keeps its slot and gets a
+        // texture without texels, which the device shades with the reference's own placeholder colour for a texture without data
         // (242, 45, 27: src/Texture.h:33-35).  README.md / INTEGRATION.md state the restriction.
-        const char *kind = (n >= 3 && bytes[0] == 0xFF && bytes[1] == 0xD8 && bytes[2] == 0xFF) ? "JPEG" : (n >= 2 && bytes[0] == 'B' && bytes[1] == 'M') ? "BMP" : "non-PNG";
-        fprintf(stderr, "SceneLoader: texture %s is a %s image; only PNG is decoded here, the placeholder colour (242, 45, 27) is used instead\n", what.c_str(), kind);
+        const char *kind = is_jpeg ? "JPEG this decoder does not cover" : (n >= 2 && bytes[0] == 'B' && bytes[1] == 'M') ? "BMP image" : "non-PNG, non-JPEG image";
+        fprintf(stderr, "SceneLoader: texture %s is a %s; the placeholder colour (242, 45, 27) is used instead\n", what.c_str(), kind);
         HostTexture t;
         t.width = 1;
         t.height = 1;

@@ -330,3 +330,53 @@ def test_host_restatement_of_the_walk_finds_the_closest_hit_on_both_node_formats
         assert ok, msg
         assert n == rays and hits > 0.9 * rays and steps_float > 5 * rays
         assert steps_quant < 1.05 * steps_float  # the looser boxes cost a few per cent more node steps, not more
+
+
+# ------------------------------------------------------------------ JPEG textures: pinned to the reference's own decoder (stb_image)
+def _gltf_with_image(tmp_path, name, image_bytes, mime):
+    import base64
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    uv = np.array([[0, 0], [1, 0], [0, 1]], np.float32)
+    blob = pos.tobytes() + uv.tobytes()
+    gltf = {
+        "asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+        "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "TEXCOORD_0": 1}, "material": 0}]}],
+        "materials": [{"name": "photo", "pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}}],
+        "textures": [{"source": 0}], "images": [{"uri": f"data:{mime};base64," + base64.b64encode(image_bytes).decode()}],
+        "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}, {"bufferView": 1, "componentType": 5126, "count": 3, "type": "VEC2"}],
+        "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 24}],
+        "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+    }
+    path = tmp_path / f"{name}.gltf"
+    path.write_text(json.dumps(gltf))
+    return path
+
+
+def test_jpeg_textures_decode_to_the_texels_of_the_references_own_decoder(ptb, core_lib, tmp_path):
+    """tests/golden/jpeg/*.jpg with, beside each, what the reference's image decoder (third-party/stb_image.h through oracle/_ref/ref_stb,
+    oracle/make_golden_jpeg.py) makes of it.  The repo's JPEG reader (csrc/host/JpegDecoder.h: stb_image's inverse DCT, chroma upsampling and
+    YCbCr -> RGB restated) must give the SAME bytes: 4:4:4 / 4:2:2 / 4:2:0, sizes that are not multiples of the MCU down to 1x1, restart
+    intervals, optimised tables, quality 5 .. 100, grey.  A progressive file is refused and becomes the placeholder texture.  When the
+    reference-derived tool is present (build container) it is also run live."""
+    import gzip
+    jdir = GOLD / "jpeg"
+    names = sorted(p.stem for p in jdir.glob("*.jpg"))
+    assert len(names) >= 12
+    stb = ROOT / "oracle" / "_ref" / "ref_stb"
+    for name in names:
+        raw = gzip.decompress((jdir / f"{name}.raw.gz").read_bytes())
+        head, body = raw.split(b"\n", 1)
+        w, h, c = (int(x) for x in head.split())
+        ref = np.frombuffer(body, np.uint8).reshape(h, w, c)
+        if stb.exists():
+            out = tmp_path / "live.raw"
+            subprocess.run([str(stb), str(jdir / f"{name}.jpg"), str(out)], check=True)
+            assert out.read_bytes() == raw, name  # the fixture is what the reference's decoder says today
+        sc = ptb.load_scene_file(_gltf_with_image(tmp_path, name, (jdir / f"{name}.jpg").read_bytes(), "image/jpeg"))
+        tex = sc.textures[0]
+        if name.startswith("progressive"):
+            assert tex.shape[0] == 0, name  # not restated: placeholder texture, the load goes on
+            continue
+        expect = ref if c == 3 else np.repeat(ref, 3, axis=2)  # grey is replicated (stbi_load(path, ..., 3) of the reference's file path)
+        assert tex.shape == (h, w, 3), (name, tex.shape)
+        assert np.array_equal(tex, expect.astype(np.float32)), (name, int((tex != expect).sum()))
