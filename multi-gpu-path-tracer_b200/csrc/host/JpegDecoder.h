@@ -1,4 +1,4 @@
-// JpegDecoder.h — baseline / extended-sequential Huffman JPEG -> 8-bit pixels, for SceneLoader's textures.
+// JpegDecoder.h — Huffman JPEG (baseline, extended-sequential, progressive) -> 8-bit pixels, for SceneLoader's textures.
 //
 // The reference decodes textures with stb_image (third-party/stb_image.h through src/HostScene.cpp:10-51, un-modified public-domain
 // code): a JPEG baseColor texture — the usual case of a photographic .glb — must come out with the SAME bytes, or every textured hit
@@ -13,7 +13,8 @@
 //                                                                                              stbi__YCbCr_to_RGB_row
 // plus its conventions: component planes padded to whole MCUs, colour images come out as 3 channels and grey ones as 1, an Adobe APP14
 // transform of 0 without JFIF (or component ids 'R','G','B') means the data are RGB already, CMYK / YCCK through (a * b + 128) / 255.
-// Progressive JPEG (SOF2) is not restated: the caller falls back to the placeholder texture for it.
+// Progressive JPEG (SOF2: spectral selection and successive approximation, coefficients kept until the end, dequantised in 16-bit
+// arithmetic and then the same inverse DCT) is restated too                                     stbi__jpeg_decode_block_prog_dc / _ac, stbi__jpeg_finish
 #pragma once
 
 #include <cstdint>
@@ -34,6 +35,7 @@ struct Component {
     int id = 0, h = 1, v = 1, tq = 0, hd = 0, ha = 0, dc_pred = 0;
     int x = 0, y = 0, w2 = 0, h2 = 0;
     std::vector<uint8_t> data;
+    std::vector<short> coeff;  // progressive: 64 coefficients per block of the padded plane, w2 / 8 blocks per row
 };
 
 class Decoder {
@@ -47,10 +49,9 @@ public:
             int m = next_marker();
             if (m < 0) return fail(err, "truncated JPEG");
             if (m == 0xD9) break;  // EOI
-            if (m == 0xC0 || m == 0xC1) {
+            if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
+                progressive_ = m == 0xC2;
                 if (!frame_header(err)) return false;
-            } else if (m == 0xC2) {
-                return fail(err, "progressive JPEG is not supported");
             } else if (m == 0xDA) {
                 if (!have_frame_) return fail(err, "scan before frame header");
                 if (!scan_header(err)) return false;
@@ -60,6 +61,7 @@ public:
             }
         }
         if (!have_frame_) return fail(err, "no frame in JPEG");
+        if (progressive_) finish_progressive();
         finish(width, height, channels, out);
         return true;
     }
@@ -205,6 +207,7 @@ private:
             c.w2 = mcu_x_ * c.h * 8;  // plane padded to whole MCUs
             c.h2 = mcu_y_ * c.v * 8;
             c.data.assign((size_t)c.w2 * (size_t)c.h2, 0);
+            if (progressive_) c.coeff.assign((size_t)c.w2 * (size_t)c.h2, 0);
         }
         have_frame_ = true;
         return true;
@@ -224,8 +227,17 @@ private:
             if (comp_[which].hd > 3 || comp_[which].ha > 3) return fail(err, "bad SOS tables");
             order_[i] = which;
         }
-        const int ss = get8(), se = get8(), a = get8();
-        if (ss != 0 || a != 0 || (se != 63 && se != 0)) return fail(err, "bad SOS (not sequential)");
+        spec_start_ = get8();
+        spec_end_ = get8();
+        const int a = get8();
+        succ_high_ = a >> 4;
+        succ_low_ = a & 15;
+        if (progressive_) {
+            if (spec_start_ > 63 || spec_end_ > 63 || spec_start_ > spec_end_ || succ_high_ > 13 || succ_low_ > 13) return fail(err, "bad SOS");
+        } else {
+            if (spec_start_ != 0 || succ_high_ != 0 || succ_low_ != 0) return fail(err, "bad SOS");
+            spec_end_ = 63;
+        }
         return true;
     }
 
@@ -237,6 +249,7 @@ private:
         for (int i = 0; i < 4; i++) comp_[i].dc_pred = 0;
         pending_marker_ = -1;
         todo_ = restart_interval_ ? restart_interval_ : 0x7fffffff;
+        eob_run_ = 0;
     }
     void fill() {
         while (nbits_ <= 24) {
@@ -307,6 +320,139 @@ private:
         return true;
     }
 
+    // ---- progressive scans: one band of one bit plane of the coefficients per scan ----
+    bool prog_dc(short *data, Component &c, std::string &err) {
+        if (spec_end_ != 0) return fail(err, "can't merge dc and ac");
+        if (succ_high_ == 0) {  // first pass of the DC term
+            memset(data, 0, 64 * sizeof(short));
+            const Huff &hd = dc_[c.hd];
+            if (!hd.ok) return fail(err, "missing Huffman table");
+            const int t = decode_symbol(hd);
+            if (t < 0 || t > 15) return fail(err, "bad Huffman code");
+            c.dc_pred += t ? receive_extend(t) : 0;
+            data[0] = (short)(c.dc_pred * (1 << succ_low_));
+        } else if (take(1)) {  // refinement: one more bit
+            data[0] += (short)(1 << succ_low_);
+        }
+        return true;
+    }
+    bool prog_ac(short *data, Component &c, std::string &err) {
+        if (spec_start_ == 0) return fail(err, "can't merge dc and ac");
+        const Huff &ha = ac_[c.ha];
+        if (!ha.ok) return fail(err, "missing Huffman table");
+        if (succ_high_ == 0) {  // first pass of this band
+            if (eob_run_) {
+                --eob_run_;
+                return true;
+            }
+            int k = spec_start_;
+            do {
+                const int rs = decode_symbol(ha);
+                if (rs < 0) return fail(err, "bad Huffman code");
+                const int s = rs & 15, r = rs >> 4;
+                if (s == 0) {
+                    if (r < 15) {  // end of band for 2^r + extra blocks
+                        eob_run_ = 1 << r;
+                        if (r) eob_run_ += take(r);
+                        --eob_run_;
+                        break;
+                    }
+                    k += 16;
+                } else {
+                    k += r;
+                    if (k > 63) return fail(err, "bad AC run");
+                    data[kZigzag[k++]] = (short)(receive_extend(s) * (1 << succ_low_));
+                }
+            } while (k <= spec_end_);
+            return true;
+        }
+        // refinement pass: one more bit for the coefficients that are already non-zero, new +-1 coefficients in between
+        const short bit = (short)(1 << succ_low_);
+        auto refine = [&](short &p) {
+            if (take(1) && (p & bit) == 0) p = (short)(p > 0 ? p + bit : p - bit);
+        };
+        if (eob_run_) {
+            --eob_run_;
+            for (int k = spec_start_; k <= spec_end_; k++) {
+                short &p = data[kZigzag[k]];
+                if (p != 0) refine(p);
+            }
+            return true;
+        }
+        int k = spec_start_;
+        do {
+            const int rs = decode_symbol(ha);
+            if (rs < 0) return fail(err, "bad Huffman code");
+            int s = rs & 15, r = rs >> 4;
+            if (s == 0) {
+                if (r < 15) {
+                    eob_run_ = (1 << r) - 1;
+                    if (r) eob_run_ += take(r);
+                    r = 64;  // to the end of the band
+                }
+            } else {
+                if (s != 1) return fail(err, "bad Huffman code");
+                s = take(1) ? bit : -bit;
+            }
+            while (k <= spec_end_) {  // advance over r zero coefficients, refining the non-zero ones on the way
+                short &p = data[kZigzag[k++]];
+                if (p != 0) {
+                    refine(p);
+                } else {
+                    if (r == 0) {
+                        p = (short)s;
+                        break;
+                    }
+                    --r;
+                }
+            }
+        } while (k <= spec_end_);
+        return true;
+    }
+    bool progressive_scan(std::string &err) {
+        bool stop;
+        if (scan_n_ == 1) {
+            Component &c = comp_[order_[0]];
+            const int w = (c.x + 7) >> 3, h = (c.y + 7) >> 3, cw = c.w2 / 8;
+            for (int j = 0; j < h; j++)
+                for (int i = 0; i < w; i++) {
+                    short *data = c.coeff.data() + 64 * ((size_t)i + (size_t)j * cw);
+                    if (!(spec_start_ == 0 ? prog_dc(data, c, err) : prog_ac(data, c, err))) return false;
+                    restart_if_due(stop);
+                    if (stop) return true;
+                }
+            return true;
+        }
+        for (int j = 0; j < mcu_y_; j++)  // interleaved scans carry DC terms only
+            for (int i = 0; i < mcu_x_; i++) {
+                for (int k = 0; k < scan_n_; k++) {
+                    Component &c = comp_[order_[k]];
+                    const int cw = c.w2 / 8;
+                    for (int y = 0; y < c.v; y++)
+                        for (int x = 0; x < c.h; x++) {
+                            short *data = c.coeff.data() + 64 * ((size_t)(i * c.h + x) + (size_t)(j * c.v + y) * cw);
+                            if (!prog_dc(data, c, err)) return false;
+                        }
+                }
+                restart_if_due(stop);
+                if (stop) return true;
+            }
+        return true;
+    }
+    void finish_progressive() {  // dequantise in 16-bit arithmetic, then the same inverse DCT
+        for (int n = 0; n < n_comp_; n++) {
+            Component &c = comp_[n];
+            const int w = (c.x + 7) >> 3, h = (c.y + 7) >> 3, cw = c.w2 / 8;
+            const uint16_t *dq = dequant_[c.tq];
+            for (int j = 0; j < h; j++)
+                for (int i = 0; i < w; i++) {
+                    short *data = c.coeff.data() + 64 * ((size_t)i + (size_t)j * cw);
+                    for (int k = 0; k < 64; k++) data[k] = (short)(data[k] * dq[k]);
+                    idct(c.data.data() + (size_t)c.w2 * j * 8 + i * 8, c.w2, data);
+                }
+        }
+    }
+
     bool restart_if_due(bool &stop) {
         stop = false;
         if (--todo_ <= 0) {
@@ -322,6 +468,7 @@ private:
 
     bool entropy_coded_data(std::string &err) {
         reset_entropy();
+        if (progressive_) return progressive_scan(err);
         short block[64];
         if (scan_n_ == 1) {  // non-interleaved: the component's own blocks, row by row
             Component &c = comp_[order_[0]];
@@ -568,7 +715,8 @@ private:
     int img_x_ = 0, img_y_ = 0, n_comp_ = 0, h_max_ = 1, v_max_ = 1, mcu_w_ = 8, mcu_h_ = 8, mcu_x_ = 0, mcu_y_ = 0;
     int scan_n_ = 0, order_[4] = {0, 0, 0, 0};
     int restart_interval_ = 0, todo_ = 0, rgb_ids_ = 0, adobe_transform_ = -1, pending_marker_ = -1;
-    bool jfif_ = false, have_frame_ = false, no_more_ = false;
+    int spec_start_ = 0, spec_end_ = 63, succ_high_ = 0, succ_low_ = 0, eob_run_ = 0;
+    bool jfif_ = false, have_frame_ = false, no_more_ = false, progressive_ = false;
     uint32_t bits_ = 0;
     int nbits_ = 0;
 };

@@ -346,7 +346,7 @@ HostTexture texture_from_bytes(const unsigned char *bytes, size_t n, const std::
     static const unsigned char png_sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     const bool is_jpeg = n >= 3 && bytes[0] == 0xFF && bytes[1] == 0xD8 && bytes[2] == 0xFF;
     if (is_jpeg) {
-        // baseline / extended-sequential JPEG: JpegDecoder.h restates the three implementation-defined steps of stb_image (IDCT, chroma
+        // JPEG (sequential and progressive): JpegDecoder.h restates the three implementation-defined steps of stb_image (IDCT, chroma
         // upsampling, YCbCr -> RGB), so the texels are the reference's byte for byte (pinned against stb_image itself: oracle/ref_stb.c)
         ptjpeg::Decoder dec;
         if (dec.decode(bytes, n, w, h, ch, px, err)) {
@@ -363,8 +363,8 @@ HostTexture texture_from_bytes(const unsigned char *bytes, size_t n, const std::
         fprintf(stderr, "SceneLoader: JPEG texture %s: %s\n", what.c_str(), err.c_str());
     }
     if (is_jpeg || n < 8 || memcmp(bytes, png_sig, 8) != 0) {
-        // The reference decodes textures with stb_image (src/HostScene.cpp:10-51), which also reads progressive JPEG / BMP / TGA / GIF / PSD /
-        // HDR; PNG and sequential JPEG are restated here.  Any other image does not abort the load: the material keeps its slot and gets a
+        // The reference decodes textures with stb_image (src/HostScene.cpp:10-51), which also reads BMP / TGA / GIF / PSD / HDR; PNG and
+        // JPEG are restated here.  Any other image does not abort the load: the material keeps its slot and gets a
         // texture without texels, which the device shades with the reference's own placeholder colour for a texture without data
         // (242, 45, 27: src/Texture.h:33-35).  README.md / INTEGRATION.md state the restriction.
         const char *kind = is_jpeg ? "JPEG this decoder does not cover" : (n >= 2 && bytes[0] == 'B' && bytes[1] == 'M') ? "BMP image" : "non-PNG, non-JPEG image";

@@ -4,7 +4,7 @@
     python oracle/make_golden_jpeg.py      (needs /root/reference for `make -C oracle _ref/ref_stb`; writes tests/golden/jpeg/)
 
 Small JPEG files written with Pillow (sizes that are not multiples of the MCU, 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0 chroma, grey, restart intervals,
-optimised Huffman tables, low and high quality, a progressive one that the reader must refuse) and, beside each, what stb_image decodes
+optimised Huffman tables, low and high quality, progressive files with and without chroma subsampling) and, beside each, what stb_image decodes
 from it: `<name>.raw.gz` = "W H C\\n" + bytes.  TEST INFRASTRUCTURE."""
 import gzip, io, subprocess, sys, tempfile
 from pathlib import Path
@@ -40,6 +40,10 @@ CASES = [  # name, w, h, mode, kwargs
     ("grey_q70_37x29", 37, 29, "L", dict(quality=70)),
     ("c420_q5_48x32", 48, 32, "RGB", dict(quality=5, subsampling=2)),
     ("progressive_q80_32x32", 32, 32, "RGB", dict(quality=80, progressive=True)),
+    ("progressive_c444_q92_45x27", 45, 27, "RGB", dict(quality=92, progressive=True, subsampling=0)),
+    ("progressive_c420_q40_61x33", 61, 33, "RGB", dict(quality=40, progressive=True, subsampling=2)),
+    ("progressive_grey_q85_19x40", 19, 40, "L", dict(quality=85, progressive=True)),
+    ("progressive_c422_rst_q75_52x36", 52, 36, "RGB", dict(quality=75, progressive=True, subsampling=1, restart_marker_blocks=3)),
 ]
 
 

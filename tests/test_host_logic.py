@@ -356,12 +356,12 @@ def test_jpeg_textures_decode_to_the_texels_of_the_references_own_decoder(ptb, c
     """tests/golden/jpeg/*.jpg with, beside each, what the reference's image decoder (third-party/stb_image.h through oracle/_ref/ref_stb,
     oracle/make_golden_jpeg.py) makes of it.  The repo's JPEG reader (csrc/host/JpegDecoder.h: stb_image's inverse DCT, chroma upsampling and
     YCbCr -> RGB restated) must give the SAME bytes: 4:4:4 / 4:2:2 / 4:2:0, sizes that are not multiples of the MCU down to 1x1, restart
-    intervals, optimised tables, quality 5 .. 100, grey.  A progressive file is refused and becomes the placeholder texture.  When the
+    intervals, optimised tables, quality 5 .. 100, grey, progressive (spectral selection + successive approximation).  When the
     reference-derived tool is present (build container) it is also run live."""
     import gzip
     jdir = GOLD / "jpeg"
     names = sorted(p.stem for p in jdir.glob("*.jpg"))
-    assert len(names) >= 12
+    assert len(names) >= 17
     stb = ROOT / "oracle" / "_ref" / "ref_stb"
     for name in names:
         raw = gzip.decompress((jdir / f"{name}.raw.gz").read_bytes())
@@ -374,9 +374,6 @@ def test_jpeg_textures_decode_to_the_texels_of_the_references_own_decoder(ptb, c
             assert out.read_bytes() == raw, name  # the fixture is what the reference's decoder says today
         sc = ptb.load_scene_file(_gltf_with_image(tmp_path, name, (jdir / f"{name}.jpg").read_bytes(), "image/jpeg"))
         tex = sc.textures[0]
-        if name.startswith("progressive"):
-            assert tex.shape[0] == 0, name  # not restated: placeholder texture, the load goes on
-            continue
         expect = ref if c == 3 else np.repeat(ref, 3, axis=2)  # grey is replicated (stbi_load(path, ..., 3) of the reference's file path)
         assert tex.shape == (h, w, 3), (name, tex.shape)
         assert np.array_equal(tex, expect.astype(np.float32)), (name, int((tex != expect).sum()))
