@@ -103,7 +103,7 @@ enum { /* ptcore_set_option keys */
     PT_OPT_BVH_LEAF_MAX = 3, /* max triangles per leaf for the next upload (default 4) */
     PT_OPT_BLOCKS_PER_SM = 4,/* persistent grid = SMs x this (0 = auto) */
     /* 5 is reserved */
-    PT_OPT_REFILL_AT = 6,    /* wavefront kernel: finished lanes per warp that trigger a shade/refill pass (1..32, default 24) */
+    PT_OPT_REFILL_AT = 6,    /* wavefront kernel: finished lanes per warp that trigger a shade/refill pass (1..32; 0 = the default, 20) */
     PT_OPT_NODE_BURST = 7,   /* wavefront kernel: node steps per warp vote (1..4) */
     PT_OPT_MIN_BLOCKS = 8,   /* accepted for compatibility: only the __launch_bounds__(128, 8) (64-register) build is shipped */
     PT_OPT_BVH_WIDTH = 9,    /* wavefront kernel: walk the 2-wide (64 B nodes, default) or the collapsed 4-wide (128 B nodes) tree; 4-wide measured 20 % slower on cornell_duck */

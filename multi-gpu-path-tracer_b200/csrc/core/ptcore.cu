@@ -70,7 +70,7 @@ struct ptcore {
     bool count_tests = false;
     int leaf_max = 4;
     int blocks_per_sm = 0;
-    int refill_at = 24;
+    int refill_at = 0;     // 0 = default (20: profiles/r02_knob_sweep.txt, +2.3 % over 24 with shared-memory nodes, +1.6 % without)
     int node_burst = 2;
     int min_blocks = 8;
     int bvh_width = 2;
@@ -397,7 +397,7 @@ int render_blocks(ptcore *h, const uint32_t *blocks_dev, uint32_t n_blocks, uint
     rp.height = h->fb_h;
     rp.spp = spp;
     rp.depth = h->depth;
-    rp.refill_at = h->refill_at;
+    rp.refill_at = h->refill_at ? h->refill_at : 20;
     rp.node_burst = h->node_burst;
     rp.lanes_per_warp = h->lanes_per_warp;
     rp.retire_log = h->retire_log;
@@ -435,7 +435,7 @@ int render_tiles(ptcore *h, const PtTile *tiles, int32_t n_tiles, cudaStream_t s
         rp.height = h->fb_h;
         rp.spp = h->spp;
         rp.depth = h->depth;
-        rp.refill_at = h->refill_at;
+        rp.refill_at = h->refill_at ? h->refill_at : 20;
         rp.node_burst = h->node_burst;
         rp.lanes_per_warp = h->lanes_per_warp;
         rp.retire_log = h->retire_log;
@@ -837,7 +837,7 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
             h->blocks_per_sm = (int)value;
             return PT_OK;
         case PT_OPT_REFILL_AT:
-            if (value < 1 || value > 32) return fail(h, PT_ERR_INVALID_ARGUMENT, "refill_at must be in [1, 32]");
+            if (value < 0 || value > 32) return fail(h, PT_ERR_INVALID_ARGUMENT, "refill_at must be in [0, 32]");
             h->refill_at = (int)value;
             return PT_OK;
         case PT_OPT_NODE_BURST:
@@ -1007,7 +1007,7 @@ int ptcore_render_keyed_async(ptcore_t *h, const uint32_t *blocks_dev, uint32_t 
     rp.height = h->fb_h;
     rp.spp = h->spp;
     rp.depth = h->depth;
-    rp.refill_at = h->refill_at;
+    rp.refill_at = h->refill_at ? h->refill_at : 20;
     rp.node_burst = h->node_burst;
     rp.lanes_per_warp = h->lanes_per_warp;
     rp.retire_log = h->retire_log;

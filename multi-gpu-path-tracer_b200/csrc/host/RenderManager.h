@@ -332,7 +332,7 @@ private:
 
     // ---- LPT: the multi-GPU schedule of the bench (sched.py: render_frame_lpt), in-process ---------------------------------------------
     // A pixel is one sequential chain of spp samples, so a frame ends when its longest chain ends.  Every GPU traces a pilot pass over
-    // 1/N of the 8x4 blocks (rays per block), the slices meet in pinned host memory, ONE thread sorts the blocks by cost and deals them
+    // 1/N of the 8x4 blocks (rays per block), the slices meet in pinned host memory, ONE thread orders the blocks by cost class and deals them
     // round-robin, every GPU renders its list most-expensive-first in one persistent launch and — if it is not the GPU that holds the
     // frame's master copy — pushes its blocks there with peer stores on the same stream.  Replaces the reference's per-frame rectangles
     // (src/RenderManager.h:264-408) for frames that are too short for feedback from the previous frame to help.
@@ -388,11 +388,9 @@ private:
         checkPtcore(dpt.core(), ptcore_block_costs_range_async(dpt.core(), kLptPilotSpp, s.dCosts, first, cnt, st));
         if (cnt) checkCudaErrors(cudaMemcpyAsync(lptHostCosts_ + first, s.dCosts + first, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, st));
         checkCudaErrors(cudaStreamSynchronize(st));
-        // 2. one thread sorts (stable, descending) and deals the blocks
+        // 2. one thread orders the blocks (cost classes, Z-order within a class) and deals them
         lptRendezvous([&] {
-            std::vector<uint32_t> order(n);
-            for (uint32_t i = 0; i < n; i++) order[i] = i;
-            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return lptHostCosts_[a] > lptHostCosts_[b]; });
+            const std::vector<uint32_t> order = TaskGenerator::lptBlockOrder(lptHostCosts_, n, bw, TaskGenerator::lptLevels(N));
             for (int k = 0; k < N; k++) lpt_[(size_t)k].blocks.clear();
             for (uint32_t i = 0; i < n; i++) lpt_[(size_t)(i % (uint32_t)N)].blocks.push_back((order[i] % bw) | ((order[i] / bw) << 16));
         });

@@ -124,6 +124,31 @@ int main() {
         auto out = gen.bisectTasksDSDL(tasks, 4, 8, 8, 8, 8);
         check((int)out.size() == 4 && tilesExactly(out, 8, 8), "DSDL with more workers than blocks");
     }
+    // LPT block order: cost classes, highest first, Z-order within a class (the literal is the one tests/test_host_logic.py checks
+    // sched.lpt_block_order against); random costs: a permutation with non-increasing classes and increasing curve index per class
+    {
+        const uint32_t costs[8] = {79, 10, 50, 30, 40, 20, 60, 0};
+        const std::vector<uint32_t> want = {0, 6, 4, 2, 5, 3, 1, 7};
+        check(TaskGenerator::lptBlockOrder(costs, 8, 4, 4) == want, "LPT block order of the 4x2 example");
+        for (uint32_t levels : {1u, 4u, 8u}) {
+            const uint32_t bw = 37, bh = 23, n = bw * bh;
+            std::vector<uint32_t> c(n);
+            uint32_t cmax = 0;
+            for (auto &v : c) { v = rng() % 5000; cmax = std::max(cmax, v); }
+            auto order = TaskGenerator::lptBlockOrder(c.data(), n, bw, levels);
+            std::vector<int> seen(n, 0);
+            bool ok = order.size() == n;
+            for (uint32_t k = 0; ok && k < n; k++) {
+                ok = order[k] < n && !seen[order[k]]++;
+                if (ok && k) {
+                    const uint64_t a = (uint64_t)c[order[k - 1]] * levels / ((uint64_t)cmax + 1), b = (uint64_t)c[order[k]] * levels / ((uint64_t)cmax + 1);
+                    ok = a > b || (a == b && TaskGenerator::zOrder(order[k - 1] % bw, order[k - 1] / bw) < TaskGenerator::zOrder(order[k] % bw, order[k] / bw));
+                }
+            }
+            check(ok, "LPT block order: permutation, classes descending, Z-order within a class");
+        }
+        check(TaskGenerator::lptBlockOrder(nullptr, 0, 1, 4).empty(), "LPT block order of an empty grid");
+    }
     printf("%s\n", failures ? "TASK_GENERATOR_TEST_FAILED" : "TASK_GENERATOR_TEST_OK");
     return failures ? 1 : 0;
 }

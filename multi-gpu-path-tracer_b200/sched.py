@@ -38,6 +38,35 @@ def interleave(tiles: List[Tile], stride: int) -> List[Tile]:
     return out
 
 
+def lpt_levels(world: int) -> int:
+    return 8 if world <= 2 else 4
+
+
+def _z_order(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    def spread(v):
+        v = v & 0xFFFF
+        v = (v | (v << 8)) & 0x00FF00FF
+        v = (v | (v << 4)) & 0x0F0F0F0F
+        v = (v | (v << 2)) & 0x33333333
+        v = (v | (v << 1)) & 0x55555555
+        return v
+    return spread(x) | (spread(y) << 1)
+
+
+def lpt_block_order(costs: torch.Tensor, bw: int, levels: int, z: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Order of the 8x4 blocks of a bw-wide grid for the LPT frame: most expensive cost CLASS first (class = cost * levels //
+    (max cost + 1)), along the Z-order curve within a class.  A full sort by cost scatters neighbouring blocks over the launch;
+    classes keep "long chains start first" and leave warps that run side by side on neighbouring pixels, i.e. on the same
+    triangles: 728 -> 700 ms per 1080p / 1024 spp frame on one GPU (profiles/r02_block_order_ab.txt).  Same function as
+    TaskGenerator::lptBlockOrder (csrc/host/TaskGenerator.h); no host synchronisation."""
+    if z is None:
+        i = torch.arange(costs.numel(), device=costs.device, dtype=torch.int64)
+        z = _z_order(i % bw, i // bw)
+    c = costs.to(torch.int64)
+    cls = (c * levels) // (c.max() + 1)
+    return torch.argsort(((levels - 1 - cls) << 32) | z)  # keys are unique
+
+
 @dataclass
 class FramePlan:
     width: int
@@ -116,7 +145,7 @@ class RankRenderer:
         Every pixel is one sequential chain of spp samples (its XORWOW stream), so the unit of work cannot be split and
         a frame ends when the last chain ends.  A pilot pass (pilot_spp samples per pixel, a few per mille of the frame)
         measures rays per 8x4 block — each rank traces 1/world of the blocks and one all-reduce (SUM of a 260 KB map)
-        gives every rank the whole map; blocks are sorted by that cost, dealt round-robin to the ranks (equal cost per
+        gives every rank the whole map; blocks are ordered by that cost (lpt_block_order), dealt round-robin to the ranks (equal cost per
         GPU: every rank computes the same order) and each GPU's persistent kernel takes its blocks most-expensive-first,
         which keeps the tail of the frame short.  `emulated`: this process stands in for rank `rank` of `world` on one
         GPU (experiments): the pilot covers the whole frame and nothing is gathered.
@@ -129,6 +158,8 @@ class RankRenderer:
         n = bw * bh
         if getattr(self, "costs", None) is None or self.costs.numel() != n:
             self.costs = torch.zeros(n, dtype=torch.int32, device=self.device)
+            i = torch.arange(n, device=self.device, dtype=torch.int64)
+            self.z_order = _z_order(i % bw, i // bw)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         distributed = world > 1 and not emulated
         with torch.cuda.stream(s):
@@ -142,7 +173,7 @@ class RankRenderer:
             else:
                 self.pt.block_costs_async(pilot_spp, self.costs.data_ptr(), s.cuda_stream)
             ev[1].record(s)
-            order = torch.argsort(self.costs, descending=True, stable=True)
+            order = lpt_block_order(self.costs, bw, lpt_levels(world), self.z_order)
             mine = order[rank::world]
             self.blocks = ((mine % bw) | ((mine // bw) << 16)).to(torch.int32).contiguous()  # kept alive until the next frame
             ev[2].record(s)
@@ -173,6 +204,8 @@ class RankRenderer:
         npix = self.width * self.height
         if getattr(self, "costs", None) is None or self.costs.numel() != n:
             self.costs = torch.zeros(n, dtype=torch.int32, device=self.device)
+            i = torch.arange(n, device=self.device, dtype=torch.int64)
+            self.z_order = _z_order(i % bw, i // bw)
         if getattr(self, "accum", None) is None or self.accum.numel() != n_chunks * npix * 3:
             self.accum = torch.zeros(n_chunks * npix * 3, dtype=torch.float32, device=self.device)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
@@ -187,7 +220,7 @@ class RankRenderer:
             else:
                 self.pt.block_costs_async(pilot_spp, self.costs.data_ptr(), s.cuda_stream)
             ev[1].record(s)
-            order = torch.argsort(self.costs, descending=True, stable=True)
+            order = lpt_block_order(self.costs, bw, lpt_levels(1), self.z_order)
             self.blocks = ((order % bw) | ((order // bw) << 16)).to(torch.int32).contiguous()
             ev[2].record(s)
             self.pt.render_keyed_async(self.accum.data_ptr(), n_chunks, rank, world, self.blocks.data_ptr(), int(self.blocks.numel()), s.cuda_stream)

@@ -310,6 +310,27 @@ def test_task_generator_and_time_driven_schedulers_tile_the_frame(core_lib):
     assert r.returncode == 0 and "TASK_GENERATOR_TEST_OK" in r.stdout, r.stdout[-800:]
 
 
+def test_lpt_block_order_is_cost_classes_then_z_order(ptb):
+    """sched.lpt_block_order (the torch side of TaskGenerator::lptBlockOrder, whose self-test holds the same literal): a permutation,
+    highest cost class first, along the Z-order curve within a class; independent of the rank that computes it."""
+    import torch
+    from ptb200 import sched
+    costs = torch.tensor([79, 10, 50, 30, 40, 20, 60, 0], dtype=torch.int32)
+    assert sched.lpt_block_order(costs, 4, 4).tolist() == [0, 6, 4, 2, 5, 3, 1, 7]
+    g = torch.Generator().manual_seed(7)
+    bw, bh = 37, 23
+    c = torch.randint(0, 5000, (bw * bh,), generator=g, dtype=torch.int32)
+    for levels in (1, 4, 8):
+        order = sched.lpt_block_order(c, bw, levels)
+        assert sorted(order.tolist()) == list(range(bw * bh))
+        cls = (c.long() * levels // (int(c.max()) + 1))[order]
+        assert bool((cls[:-1] >= cls[1:]).all())
+        z = sched._z_order(order % bw, order // bw)
+        same = cls[:-1] == cls[1:]
+        assert bool((z[:-1][same] < z[1:][same]).all())
+    assert sched.lpt_levels(1) == 8 and sched.lpt_levels(8) == 4
+
+
 def test_argument_loader_positionals_flags_and_errors(core_lib):
     """csrc/host/ArgumentLoader.h: the reference's two positionals with their defaults (src/ArgumentLoader.h:10-13), every added
     flag, and exceptions that name the offending argument."""
