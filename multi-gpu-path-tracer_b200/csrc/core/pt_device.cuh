@@ -304,6 +304,9 @@ constexpr int kStackSize = 64;
 // zero to 2^-80 (sign kept); the slab distances then belong to a ray that is off by < 1e-18 scene units over any
 // t the scene allows, far inside the boxes' host-side padding, so the test stays conservative.  Only the BOX
 // tests see this: the primitive tests use the unmodified direction, as the reference does.
+#ifndef PT_SLAB_RCP_APPROX
+#define PT_SLAB_RCP_APPROX 1
+#endif
 __device__ __forceinline__ float3 slab_inverse(float3 d) {
     const float kTiny = 8.271806125530277e-25f;  // 2^-80
     const float dx = fabsf(d.x) < kTiny ? copysignf(kTiny, d.x) : d.x;
@@ -312,11 +315,15 @@ __device__ __forceinline__ float3 slab_inverse(float3 d) {
     // box tests only steer the walk (every hit is decided by the primitive tests, which use the exact direction), and the boxes are padded by
     // 1e-5 of their coordinates on the host: the one-ulp error of MUFU.RCP is far inside that, and one instruction replaces the ~10 of an
     // IEEE division, three times per ray (1.7 % of the executed instructions in profiles/r02_ncu_wavefront_source_lines.txt)
+#if PT_SLAB_RCP_APPROX
     float ix, iy, iz;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"(dx));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(dy));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(dz));
     return f3(ix, iy, iz);
+#else
+    return f3(1.0f / dx, 1.0f / dy, 1.0f / dz);
+#endif
 }
 
 template <bool SPHERES, bool COUNT>
@@ -611,13 +618,16 @@ __device__ __forceinline__ void trav_node_step4(const DevScene &sc, Trav &t, con
     const float4 lox = __ldg(nd + 0), hix = __ldg(nd + 1), loy = __ldg(nd + 2), hiy = __ldg(nd + 3), loz = __ldg(nd + 4), hiz = __ldg(nd + 5);
     const int4 refs = __ldg(reinterpret_cast<const int4 *>(nd + 6));
     if (COUNT) n_box += 4;
+    // an unused slot (all planes +inf, bvh_builder.cpp emptySlot) passes the slab test of a ray with inv > 0 while nothing has been hit yet
+    // (far = FLT_MAX * slack = +inf): it is excluded by its reference — an empty leaf in `cur` behind an empty held leaf would never be stepped
+    constexpr int32_t kEmptyLeaf = -1;  // leaf_ref(0, 0)
 #define PT_SLAB4(c)                                                                                                   \
     const float ax##c = fmaf(lox.c, t.inv.x, t.oinv.x), bx##c = fmaf(hix.c, t.inv.x, t.oinv.x);                       \
     const float ay##c = fmaf(loy.c, t.inv.y, t.oinv.y), by##c = fmaf(hiy.c, t.inv.y, t.oinv.y);                       \
     const float az##c = fmaf(loz.c, t.inv.z, t.oinv.z), bz##c = fmaf(hiz.c, t.inv.z, t.oinv.z);                       \
     const float tn##c = fmaxf(fmaxf(fminf(ax##c, bx##c), fminf(ay##c, by##c)), fmaxf(fminf(az##c, bz##c), tmin));     \
     const float tf##c = fminf(fminf(fmaxf(ax##c, bx##c), fmaxf(ay##c, by##c)), fminf(fmaxf(az##c, bz##c), t.best.t)); \
-    const bool h##c = tn##c <= tf##c * kSlack;
+    const bool h##c = tn##c <= tf##c * kSlack && refs.c != kEmptyLeaf;
     PT_SLAB4(x)
     PT_SLAB4(y)
     PT_SLAB4(z)
