@@ -711,6 +711,7 @@ const char *check_walks(const BvhBuildResult &bvh, const std::vector<QuantNode> 
             uint64_t steps = 0;
             while (!(cur == kDone && !held())) {
                 if (++steps > 100000) return "the walk does not terminate";
+                if (cur < 0 && !held()) return "the walk stalls: a leaf waits in cur while no leaf is held (neither vote of the kernel would step this lane)";
                 if (cur >= 0) {  // trav_node_step
                     const FlatNode &n = bvh.nodes[(size_t)cur];
                     const QuantNode &qn = q[(size_t)cur];
@@ -766,6 +767,65 @@ const char *check_walks(const BvhBuildResult &bvh, const std::vector<QuantNode> 
                 if (sp < 0) return "the walk underflows the stack";
             }
             found[mode] = best;
+        }
+        // 4. the walk on four-wide nodes (trav_node_step4 + trav_prim_step2), when the collapsed tree fits the device stack
+        if (!bvh.nodes4.empty() && bvh.stack4 <= 64) {
+            float inv[3], oinv[3];
+            for (int k = 0; k < 3; k++) {
+                inv[k] = slab_inv1(d[k]);
+                oinv[k] = -o[k] * inv[k];
+            }
+            HostHit best;
+            int32_t stack[64];
+            int32_t sp = 0, cur = 0, leaf = 0;
+            stack[sp++] = kDone;
+            auto held = [&]() { return (leaf & 15) != 0; };
+            uint64_t steps = 0;
+            while (!(cur == kDone && !held())) {
+                if (++steps > 100000) return "the four-wide walk does not terminate";
+                if (cur < 0 && !held()) return "the four-wide walk stalls: a leaf waits in cur while no leaf is held";
+                if (cur >= 0) {
+                    const FlatNode4 &n = bvh.nodes4[(size_t)cur];
+                    uint32_t key[4];
+                    for (int c = 0; c < 4; c++) {
+                        const float ax = std::fmaf(n.lox[c], inv[0], oinv[0]), bx = std::fmaf(n.hix[c], inv[0], oinv[0]);
+                        const float ay = std::fmaf(n.loy[c], inv[1], oinv[1]), by = std::fmaf(n.hiy[c], inv[1], oinv[1]);
+                        const float az = std::fmaf(n.loz[c], inv[2], oinv[2]), bz = std::fmaf(n.hiz[c], inv[2], oinv[2]);
+                        const float tn = std::fmax(std::fmax(std::fmin(ax, bx), std::fmin(ay, by)), std::fmax(std::fmin(az, bz), tmin));
+                        const float tf = std::fmin(std::fmin(std::fmax(ax, bx), std::fmax(ay, by)), std::fmin(std::fmax(az, bz), best.t));
+                        const bool hit = tn <= tf * kSlack && n.ref[c] != leaf_ref(0, 0);  // unused slots are excluded by reference
+                        uint32_t bits;
+                        std::memcpy(&bits, &tn, 4);
+                        key[c] = hit ? ((bits & ~3u) | (uint32_t)c) : 0xffffffffu;
+                    }
+                    std::sort(key, key + 4);
+                    for (int c = 3; c >= 1; c--)
+                        if (key[c] != 0xffffffffu) {
+                            if (sp >= 64) return "the four-wide walk overflows the stack";
+                            stack[sp++] = n.ref[key[c] & 3u];
+                        }
+                    int32_t next = key[0] != 0xffffffffu ? n.ref[key[0] & 3u] : stack[--sp];
+                    if (next < 0 && next != kDone && !held()) {
+                        leaf = ~next;
+                        next = stack[--sp];
+                    }
+                    cur = next;
+                } else {
+                    const int32_t k = leaf >> 4;
+                    const bool two = (leaf & 15) >= 2;
+                    float t, u, v;
+                    if (host_triangle(tri(k), o, d, tmin, t, u, v)) host_accept(best, t, u, v, k);
+                    if (two && host_triangle(tri(k + 1), o, d, tmin, t, u, v)) host_accept(best, t, u, v, k + 1);
+                    leaf += two ? 30 : 15;
+                    if (!held() && cur < 0 && cur != kDone) {
+                        leaf = ~cur;
+                        cur = stack[--sp];
+                    }
+                }
+                if (sp < 0) return "the four-wide walk underflows the stack";
+            }
+            if (best.prim != brute.prim || best.t != brute.t || best.u != brute.u || best.v != brute.v)
+                return "the walk over four-wide nodes and the test of every triangle disagree";
         }
         counts[0]++;
         counts[1] += brute.prim >= 0;

@@ -573,6 +573,17 @@ def test_absent_child_of_a_single_leaf_scene_is_never_tested(tracer, ptb, oracle
         assert st["rays"] > 0 and st["tri_tests"] <= st["rays"], (kernel, st["tri_tests"], st["rays"])
         ref, _, _ = oracle.render(sc, 64, 36, 2, 4)
         assert np.array_equal(rgb, ref)  # an emitter seen directly: no rounding-sensitive bounce
+    # the same on the four-wide root (three unused slots: a ray that has hit nothing yet passes their +inf box, so the step excludes
+    # them by reference — it once stalled there) and on float / quantised two-wide nodes
+    for width, fmt in ((4, ptb.PT_NODES_AUTO), (2, ptb.PT_NODES_FULL), (2, ptb.PT_NODES_QUANTISED)):
+        tracer.set_option(ptb.PT_OPT_BVH_WIDTH, width)
+        tracer.set_option(ptb.PT_OPT_NODE_FORMAT, fmt)
+        tracer.reset_stats()
+        rgb, _ = render(tracer, sc, 64, 36, 2, 4, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
+        st = tracer.stats()
+        assert np.array_equal(rgb, ref) and st["tri_tests"] <= st["rays"], (width, fmt, st["tri_tests"], st["rays"])
+    tracer.set_option(ptb.PT_OPT_BVH_WIDTH, 2)
+    tracer.set_option(ptb.PT_OPT_NODE_FORMAT, ptb.PT_NODES_AUTO)
     tracer.set_option(ptb.PT_OPT_KERNEL, ptb.PT_KERNEL_PERSISTENT)
 
 

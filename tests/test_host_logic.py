@@ -343,14 +343,21 @@ def test_argument_loader_positionals_flags_and_errors(core_lib):
 
 def test_host_restatement_of_the_walk_finds_the_closest_hit_on_both_node_formats(ptb, core_lib, duck, box):
     """pt_walk_selftest: the kernel's resumable walk (held leaf, sentinel stack, two-primitive leaf step, tie rule) restated on
-    the host, on float and on quantised planes, against a test of every triangle — camera-like, bounce-like (origin on a
-    triangle), vertex-aimed and axis-parallel rays."""
+    the host, on float planes, on quantised planes and on the four-wide nodes, against a test of every triangle — camera-like,
+    bounce-like (origin on a triangle), vertex-aimed and axis-parallel rays.  A lane state that neither of the kernel's two votes
+    would step (a leaf waiting in `cur` with no leaf held: the stall an accepted unused four-wide slot once caused) is an error."""
     mesh = ptb.scenes.displaced_sphere_in_cornell(duck, n=40)
     for scene, rays, seed in ((duck, 12000, 1), (box, 6000, 2), (mesh, 6000, 3)):
         ok, msg, (n, hits, steps_float, steps_quant) = ptb.walk_selftest(scene, rays, seed)
         assert ok, msg
         assert n == rays and hits > 0.9 * rays and steps_float > 5 * rays
         assert steps_quant < 1.05 * steps_float  # the looser boxes cost a few per cent more node steps, not more
+    # one triangle: the root's second child is absent, the four-wide root has three unused slots
+    import numpy as np
+    one = ptb.Scene(tri_pos=np.array([[-1, -1, -3, 1, -1, -3, 0, 1, -3]], np.float32), tri_uv=np.zeros((1, 6), np.float32), tri_mat=np.zeros(1, np.int32),
+                    mats=np.array([(ptb.PT_MAT_UNIVERSAL, (0.5, 0.5, 0.5), (1, 1, 1), -1, -1, 0, 1.5)], ptb.MAT_DTYPE))
+    ok, msg, (n, hits, _, _) = ptb.walk_selftest(one, 4000, 4)
+    assert ok and n == 4000 and hits > 0, msg
 
 
 # ------------------------------------------------------------------ JPEG textures: pinned to the reference's own decoder (stb_image)
