@@ -211,6 +211,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="override for quick experiments (a non-default value is flagged in config)")
     ap.add_argument("--kernel", default="persistent", choices=["persistent", "direct", "lockstep", "pool"])
+    ap.add_argument("--cta-warps", type=int, default=0, help="shared-memory-node kernel: warps per SM (0 = library default, chosen per launch from its pixel count)")
     ap.add_argument("--smem-nodes", type=int, default=-1, help="1024-thread wavefront kernel with the quantised nodes in shared memory (-1 = library default)")
     ap.add_argument("--refill-at", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
@@ -271,6 +272,8 @@ def main():
     pt.set_option(ptb200.PT_OPT_KERNEL, {"persistent": ptb200.PT_KERNEL_PERSISTENT, "direct": ptb200.PT_KERNEL_DIRECT, "lockstep": ptb200.PT_KERNEL_LOCKSTEP, "pool": ptb200.PT_KERNEL_POOL}[args.kernel])
     if args.smem_nodes >= 0:
         pt.set_option(ptb200.PT_OPT_SMEM_NODES, args.smem_nodes)
+    if args.cta_warps:
+        pt.set_option(ptb200.PT_OPT_CTA_WARPS, args.cta_warps)
     if args.refill_at:
         pt.set_option(ptb200.PT_OPT_REFILL_AT, args.refill_at)
     if args.blocks_per_sm:

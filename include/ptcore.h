@@ -118,6 +118,8 @@ enum { /* ptcore_set_option keys */
     PT_OPT_STICKY_TEXTURES = 19, /* next ptcore_upload_scene: 1 (default) = a UNIVERSAL material without a texture inherits the last texture index seen, as the reference's loadMaterials does (src/DevicePathTracer.h:269-279); 0 = indices as given */
     PT_OPT_RNG_MODE = 20,    /* PT_RNG_*: which random stream ptcore_render_frame_host uses (the explicit ptcore_render_keyed_async is always keyed) */
     PT_OPT_RNG_CHUNKS = 21,  /* PT_RNG_SAMPLE_KEYED through ptcore_render_frame_host: work items per pixel (default 16) */
+    PT_OPT_GRID_CTAS = 23,   /* wavefront kernels: CTAs per launch (0 = default: one per SM, or SMs x occupancy for the 128-thread kernels) */
+    PT_OPT_CTA_WARPS = 24,   /* shared-memory-node kernel: warps per CTA = per SM, 1..32 (0 = default: by the launch's pixel count — 32 for a full frame, down to 12 for launches with under ~3 pixels per lane, whose sequential sample chains end sooner on fewer warps) */
     PT_OPT_L2_PERSIST_NODES = 22, /* 1 = mark the node array persisting in L2 (access-policy window on the launch stream); for scenes larger than L2 */
     PT_OPT_WATCHDOG = 14     /* pool kernel, debugging aid: bound on the traverse iterations of a warp (0 = none); a launch that hits it renders garbage instead of hanging */
 };

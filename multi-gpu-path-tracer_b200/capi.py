@@ -26,6 +26,7 @@ PT_KERNEL_PERSISTENT, PT_KERNEL_DIRECT, PT_KERNEL_LOCKSTEP, PT_KERNEL_POOL = 0, 
 PT_OPT_NODE_FORMAT = 10
 PT_OPT_SAH_INTERSECT_COST = 11
 PT_OPT_POOL_SLOTS, PT_OPT_POOL_IDLE_AT, PT_OPT_WATCHDOG, PT_OPT_POOL_PERIOD, PT_OPT_POOL_CARVEOUT, PT_OPT_SMEM_NODES, PT_OPT_LANES_PER_WARP, PT_OPT_STICKY_TEXTURES, PT_OPT_RNG_MODE, PT_OPT_RNG_CHUNKS, PT_OPT_L2_PERSIST_NODES = 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22
+PT_OPT_GRID_CTAS, PT_OPT_CTA_WARPS = 23, 24
 PT_RNG_STREAM, PT_RNG_SAMPLE_KEYED = 0, 1
 PT_NODES_AUTO, PT_NODES_FULL, PT_NODES_QUANTISED = 0, 1, 2
 

@@ -387,7 +387,7 @@ constexpr int kSmemKernelThreads = 1024;
 template <bool SPHERES, bool RTOW, bool COUNT, bool KEYED = false>
 __global__ void __launch_bounds__(kSmemKernelThreads, 1) pt_wavefront_smem_kernel(const __grid_constant__ RenderParams p, const int32_t n_nodes) {
     extern __shared__ uint4 smem_nodesq[];  // [2 * n_nodes] quantised nodes, then [32 warps][kWfStackK][32 lanes] stack words
-    for (int i = (int)threadIdx.x; i < n_nodes * 2; i += kSmemKernelThreads) smem_nodesq[i] = __ldg(&p.scene.nodesq[i]);
+    for (int i = (int)threadIdx.x; i < n_nodes * 2; i += (int)blockDim.x) smem_nodesq[i] = __ldg(&p.scene.nodesq[i]);
     __syncthreads();
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_nodesq);
     const uint32_t stacks = base + (uint32_t)n_nodes * 32u + (threadIdx.x >> 5) * (uint32_t)(kWfStackK * 128);

@@ -86,6 +86,8 @@ struct ptcore {
     uint32_t retire_log_warps = 0;
     int smem_nodes = 1;    // wavefront kernel: 1 (default) = one 1024-thread CTA per SM with the quantised nodes in shared memory when they fit, 0 = never
     int smem_nodes_max_bytes = 160 * 1024;
+    int grid_ctas = 0;     // wavefront kernels: CTAs of the launch (0 = one per SM / SMs x occupancy)
+    int cta_warps = 0;     // shared-memory-node kernel: warps per CTA (0 = auto by the launch's pixel count, smem_cta_warps)
     int pool_slots = 0;    // 0 = auto (pixels per warp of the launch, clamped to 32 .. kPoolSlots)
     int pool_idle_at = 8;
     int pool_period = 2;
@@ -231,6 +233,18 @@ cudaError_t launch_pool(ptcore *h, RenderParams rp, cudaStream_t stream) {
     return e != cudaSuccess ? e : e2;
 }
 
+// Warps per CTA (= per SM) of the shared-memory-node kernel.  A pixel is one sequential chain of spp samples and a chain advances 2.3x faster
+// when its warp has a scheduler to itself than among 8 warps per scheduler, while the SM's throughput only needs ~5 warps per scheduler: a
+// launch with fewer than ~3 pixels per lane (a 1/8 share of a 1080p frame, a 640x360 frame) is bound by its chains, not by throughput, and
+// ends sooner on fewer, faster warps — 170 -> 160 ms for the 8-GPU share with 20 instead of 32 (profiles/r02_express_lane_ab.txt).
+// Auto: pixels / (SMs x 32 lanes x 2.7), clamped to [12, 32]; full frames on one GPU and launches of under 64 spp keep 32.
+static int smem_cta_warps(const ptcore *h, uint32_t pixels, uint32_t spp) {
+    if (h->cta_warps) return h->cta_warps;
+    if (spp < 64) return 32;  // short chains (the pilot pass): nothing to shorten
+    const double w = (double)pixels / ((double)h->sm_count * 32.0 * 2.7);
+    return (int)std::min(32.0, std::max(12.0, std::floor(w + 0.5)));
+}
+
 template <bool S, bool R, bool C>
 cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaStream_t stream) {
     const uint32_t total = rp.tiles.first_item[rp.tiles.n];
@@ -242,11 +256,14 @@ cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaS
         const size_t bytes = (size_t)h->blob.n_nodes * 32 + (kWfSmemStack ? (size_t)(kSmemKernelThreads / 32) * kWfStackK * 128 : 0);  // nodes (+ the warps' short stacks)
         cudaError_t e = cudaFuncSetAttribute(pt_wavefront_smem_kernel<S, R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
-        uint32_t grid = (uint32_t)h->sm_count;
-        const uint32_t per_cta = (uint32_t)(kSmemKernelThreads / 32 * h->lanes_per_warp);
+        // PT_OPT_GRID_CTAS / PT_OPT_CTA_WARPS: an "express" launch of a few small CTAs (one warp per scheduler) for the longest chains, beside a
+        // main launch that leaves those SMs free (sched.py: render_frame_lpt, express)
+        const uint32_t threads = 32u * (uint32_t)smem_cta_warps(h, total, rp.spp);
+        uint32_t grid = h->grid_ctas ? (uint32_t)h->grid_ctas : (uint32_t)h->sm_count;
+        const uint32_t per_cta = threads / 32u * (uint32_t)h->lanes_per_warp;
         const uint32_t needed = (total + per_cta - 1) / per_cta;
         if (grid > needed) grid = needed;
-        pt_wavefront_smem_kernel<S, R, C><<<grid, kSmemKernelThreads, bytes, stream>>>(rp, h->blob.n_nodes);
+        pt_wavefront_smem_kernel<S, R, C><<<grid, threads, bytes, stream>>>(rp, h->blob.n_nodes);
         return cudaGetLastError();
     }
     if (direct) {
@@ -261,7 +278,7 @@ cudaError_t launch_variant(ptcore *h, const RenderParams &rp, bool direct, cudaS
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
         if (h->blocks_per_sm > 0) occ = std::min(occ, h->blocks_per_sm);
-        uint32_t grid = (uint32_t)h->sm_count * (uint32_t)occ;
+        uint32_t grid = h->grid_ctas ? (uint32_t)h->grid_ctas : (uint32_t)h->sm_count * (uint32_t)occ;
         const uint32_t per_cta = (uint32_t)(kBlockThreads / 32 * (h->kernel == PT_KERNEL_PERSISTENT ? h->lanes_per_warp : 32));
         uint32_t needed = (total + per_cta - 1) / per_cta;
         if (grid > needed) grid = needed;
@@ -884,6 +901,14 @@ int ptcore_set_option(ptcore_t *h, int key, int64_t value) {
         case PT_OPT_LANES_PER_WARP:
             if (value < 1 || value > 32) return fail(h, PT_ERR_INVALID_ARGUMENT, "lanes_per_warp must be in [1, 32]");
             h->lanes_per_warp = (int)value;
+            return PT_OK;
+        case PT_OPT_GRID_CTAS:
+            if (value < 0 || value > 65535) return fail(h, PT_ERR_INVALID_ARGUMENT, "grid_ctas must be in [0, 65535]");
+            h->grid_ctas = (int)value;
+            return PT_OK;
+        case PT_OPT_CTA_WARPS:
+            if (value < 0 || value > 32) return fail(h, PT_ERR_INVALID_ARGUMENT, "cta_warps must be in [0, 32]");
+            h->cta_warps = (int)value;
             return PT_OK;
         case PT_OPT_STICKY_TEXTURES: h->sticky_textures = value != 0; return PT_OK;
         case PT_OPT_L2_PERSIST_NODES: h->l2_persist_nodes = value != 0; return PT_OK;

@@ -449,6 +449,18 @@ def test_pool_kernel_and_shared_memory_nodes_equal_the_wavefront_kernel(tracer, 
         tracer.set_option(ptb.PT_OPT_LANES_PER_WARP, 32)
         for img, y in ((c, yc), (d, yd), (e, ye)):
             assert np.array_equal(a, img) and np.array_equal(ya, y)
+        # the shape of the launch (warps per CTA of the shared-memory-node kernel, CTAs per launch; spp >= 64 lets the automatic rule pick)
+        tracer.set_option(ptb.PT_OPT_SMEM_NODES, 1)
+        for warps, ctas in ((4, 3), (12, 0), (32, 7), (1, 1), (0, 0)):
+            tracer.set_option(ptb.PT_OPT_CTA_WARPS, warps)
+            tracer.set_option(ptb.PT_OPT_GRID_CTAS, ctas)
+            g, yg = render(tracer, scene, w, h, spp, depth, cam, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
+            assert np.array_equal(a, g) and np.array_equal(ya, yg), (warps, ctas)
+        a64, _ = render(tracer, scene, w // 2, h // 2, 64, depth, cam, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
+        tracer.set_option(ptb.PT_OPT_CTA_WARPS, 32)
+        b64, _ = render(tracer, scene, w // 2, h // 2, 64, depth, cam, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)
+        tracer.set_option(ptb.PT_OPT_CTA_WARPS, 0)
+        assert np.array_equal(a64, b64)
     # pool kernel on a cost-sorted block list split in two, full-size frame
     w, h, spp, depth = 1920, 1080, 8, 10
     full, yfull = render(tracer, duck, w, h, spp, depth, kernel=ptb.PT_KERNEL_PERSISTENT, ptb=ptb)

@@ -11,6 +11,7 @@ import ptb200
 
 quick = "--quick" in sys.argv
 refill = int(sys.argv[sys.argv.index("--refill") + 1]) if "--refill" in sys.argv else 0
+cta_warps = int(sys.argv[sys.argv.index("--cta-warps") + 1]) if "--cta-warps" in sys.argv else 0
 only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else ""
 dev = torch.device("cuda", 0)
 duck = ptb200.load_scene_file(ROOT / "tests/golden/cornell_duck.ptscene.gz")
@@ -22,6 +23,7 @@ def run(name, scene, w, h, spp, depth, cam=None, reps=2):
         return
     pt = ptb200.PathTracer(0)
     pt.set_option(ptb200.PT_OPT_REFILL_AT, refill)
+    pt.set_option(ptb200.PT_OPT_CTA_WARPS, cta_warps)
     t0 = time.perf_counter(); pt.upload_scene(scene); up = time.perf_counter() - t0
     pt.set_camera(**(cam or {})); pt.set_params(spp, depth)
     rr = ptb200.sched.RankRenderer(pt, w, h, dev)
@@ -48,4 +50,4 @@ mesh = ptb200.scenes.displaced_sphere_in_cornell(duck, n=300 if quick else 1000)
 run("config4_2Mtri_mesh_4k_s256", mesh, 3840, 2160, 16 if quick else 256, 10)
 run("config5_duck_4k_s4096" if not quick else "config5_duck_4k_s256", duck, 3840, 2160, 256 if quick else 4096, 10, reps=0 if not quick else 1)
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
-(ROOT / "gpurun_out" / ("configs.json" if not (only or refill) else f"configs_{only}_refill{refill}.json")).write_text(json.dumps(out, indent=1))
+(ROOT / "gpurun_out" / ("configs.json" if not (only or refill or cta_warps) else f"configs_{only}_refill{refill}_warps{cta_warps}.json")).write_text(json.dumps(out, indent=1))
