@@ -15,6 +15,7 @@
 // Parity for this stage is pinned by SURVEY.md Appendix A (counts, bounds,
 // first/last triangles), not by the reference (it has no tests): "parity unpinned".
 #include "HostScene.h"
+#include "BmpTgaDecoder.h"
 #include "JpegDecoder.h"
 
 #include <zlib.h>
@@ -362,12 +363,30 @@ HostTexture texture_from_bytes(const unsigned char *bytes, size_t n, const std::
         }
         fprintf(stderr, "SceneLoader: JPEG texture %s: %s\n", what.c_str(), err.c_str());
     }
-    if (is_jpeg || n < 8 || memcmp(bytes, png_sig, 8) != 0) {
-        // The reference decodes textures with stb_image (src/HostScene.cpp:10-51), which also reads BMP / TGA / GIF / PSD / HDR; PNG and
-        // JPEG are restated here.  Any other image does not abort the load: the material keeps its slot and gets a
+    const bool is_png = n >= 8 && memcmp(bytes, png_sig, 8) == 0;
+    if (!is_jpeg && !is_png) {
+        // BMP and TGA (texture files of an .mtl / .gltf): BmpTgaDecoder.h restates stb_image's choices for stbi_load(path, ..., 3), the call
+        // the reference makes for files (src/HostScene.cpp:29); byte-identical texels, tests/golden/images/.  stb_image probes BMP before TGA
+        // (TGA has no signature and is its last resort); GIF / PSD / PIC / PNM / HDR, which it probes in between, all fail the TGA test.
+        const bool bmp = ptimg::is_bmp(bytes, n);
+        if (bmp || ptimg::is_tga(bytes, n)) {
+            if (bmp ? ptimg::decode_bmp(bytes, n, w, h, px, err) : ptimg::decode_tga(bytes, n, w, h, px, err)) {
+                HostTexture t;
+                t.width = w;
+                t.height = h;
+                t.data.resize((size_t)w * (size_t)h);
+                for (size_t j = 0; j < t.data.size(); j++) t.data[j] = make_float3((float)px[3 * j], (float)px[3 * j + 1], (float)px[3 * j + 2]);
+                return t;
+            }
+            fprintf(stderr, "SceneLoader: %s texture %s: %s\n", bmp ? "BMP" : "TGA", what.c_str(), err.c_str());
+        }
+    }
+    if (is_jpeg || !is_png) {
+        // The reference decodes textures with stb_image (src/HostScene.cpp:10-51), which also reads GIF / PSD / PIC / PNM / HDR; PNG, JPEG,
+        // BMP and TGA are restated here.  Any other image (or a variant stb_image refuses too, e.g. RLE BMP) does not abort the load: the material keeps its slot and gets a
         // texture without texels, which the device shades with the reference's own placeholder colour for a texture without data
         // (242, 45, 27: src/Texture.h:33-35).  README.md / INTEGRATION.md state the restriction.
-        const char *kind = is_jpeg ? "JPEG this decoder does not cover" : (n >= 2 && bytes[0] == 'B' && bytes[1] == 'M') ? "BMP image" : "non-PNG, non-JPEG image";
+        const char *kind = is_jpeg ? "JPEG this decoder does not cover" : (n >= 2 && bytes[0] == 'B' && bytes[1] == 'M') ? "BMP variant that is not decoded" : "image format other than PNG / JPEG / BMP / TGA";
         fprintf(stderr, "SceneLoader: texture %s is a %s; the placeholder colour (242, 45, 27) is used instead\n", what.c_str(), kind);
         HostTexture t;
         t.width = 1;
@@ -795,7 +814,7 @@ HostScene SceneLoader::loadOBJ(const std::string &path) {
     size_t slash = path.find_last_of('/');
     std::string dir = slash == std::string::npos ? std::string(".") : path.substr(0, slash);
 
-    struct Mtl { std::string name; float3 Ka{0, 0, 0}, Kd{0.6f, 0.6f, 0.6f}, Ke{0, 0, 0}; float Ns = 0.f, Ni = 1.5f; };
+    struct Mtl { std::string name; float3 Ka{0, 0, 0}, Kd{0.6f, 0.6f, 0.6f}, Ke{0, 0, 0}; float Ns = 0.f, Ni = 1.5f; std::string map_Kd, map_Ke; };
     std::vector<Mtl> mtls;
     auto loadMtl = [&](const std::string &file) {
         std::ifstream m(dir + "/" + file);
@@ -812,6 +831,11 @@ HostScene SceneLoader::loadOBJ(const std::string &path) {
             else if (k == "Ke") ss >> mtls.back().Ke.x >> mtls.back().Ke.y >> mtls.back().Ke.z;
             else if (k == "Ns") ss >> mtls.back().Ns;
             else if (k == "Ni") ss >> mtls.back().Ni;
+            else if (k == "map_Kd" || k == "map_Ke") {  // the file name is the last word (options such as -s 1 1 1 may precede it)
+                std::string word, file;
+                while (ss >> word) file = word;
+                (k == "map_Kd" ? mtls.back().map_Kd : mtls.back().map_Ke) = file;
+            }
         }
     };
 
@@ -820,6 +844,25 @@ HostScene SceneLoader::loadOBJ(const std::string &path) {
     std::vector<float2> T;
     std::map<std::string, int> matIndex;
     int curMat = -1;
+    // Texture files of the .mtl, decoded like the reference's stbi_load(path, ..., 3) (src/HostScene.cpp:29: PNG / JPEG / BMP / TGA here).
+    // assimp hands an OBJ's map_Kd over as aiTextureType_DIFFUSE and its map_Ke as aiTextureType_EMISSIVE; the reference loads every
+    // texture (loadTextures, :52-72) but binds only BASE_COLOR and EMISSIVE (processMaterial, :174-184) — so map_Ke becomes the emissive
+    // texture, map_Kd takes a slot in the texture list and is bound to nothing.  A missing file aborts the load, as there.
+    std::map<std::string, int> texIndex;
+    auto textureFor = [&](const std::string &file) -> int {
+        auto it = texIndex.find(file);
+        if (it != texIndex.end()) return it->second;
+        std::vector<unsigned char> bytes;
+        try {
+            bytes = read_file(dir + "/" + file);
+        } catch (const std::exception &) {
+            throw std::runtime_error("Cannot load texture data, path: " + file);
+        }
+        const int idx = (int)scene.textures.size();
+        scene.textures.push_back(texture_from_bytes(bytes.data(), bytes.size(), file));
+        texIndex[file] = idx;
+        return idx;
+    };
     auto materialFor = [&](const std::string &name) -> int {
         auto it = matIndex.find(name);
         if (it != matIndex.end()) return it->second;
@@ -837,6 +880,8 @@ HostScene SceneLoader::loadOBJ(const std::string &path) {
             case DIFFUSE_LIGHT: hm.baseColor = make_float3(0, 0, 0); hm.emissiveFactor = src->Kd; break;
             default: hm.baseColor = src->Kd; hm.emissiveFactor = src->Ke; break;
         }
+        if (!src->map_Kd.empty()) textureFor(src->map_Kd);
+        if (!src->map_Ke.empty()) hm.emissiveTextureIdx = textureFor(src->map_Ke);
         int idx = (int)scene.materials.size();
         scene.materials.push_back(hm);
         matIndex[name] = idx;

@@ -405,3 +405,55 @@ def test_jpeg_textures_decode_to_the_texels_of_the_references_own_decoder(ptb, c
         expect = ref if c == 3 else np.repeat(ref, 3, axis=2)  # grey is replicated (stbi_load(path, ..., 3) of the reference's file path)
         assert tex.shape == (h, w, 3), (name, tex.shape)
         assert np.array_equal(tex, expect.astype(np.float32)), (name, int((tex != expect).sum()))
+
+
+def test_bmp_and_tga_textures_decode_to_the_texels_of_the_references_own_decoder(ptb, core_lib, tmp_path):
+    """tests/golden/images/*.bmp|tga with, beside each, what the reference's decoder returns for a texture FILE (stb_image with three
+    requested channels, src/HostScene.cpp:29; oracle/make_golden_images.py).  csrc/host/BmpTgaDecoder.h must give the SAME bytes for every
+    header size, bit depth, palette, mask, orientation and RLE variant there — including stb_image's own quirk for a gap between a BMP
+    header and its pixels — and must refuse (placeholder texture) what stb_image refuses.  When the reference-derived tool is present
+    (build container) it is also run live."""
+    import gzip
+    idir = GOLD / "images"
+    files = sorted(p for p in idir.iterdir() if p.suffix in (".bmp", ".tga"))
+    refused = json.loads((idir / "refused.json").read_text())
+    assert len(files) >= 35 and len(refused) >= 1
+    stb = ROOT / "oracle" / "_ref" / "ref_stb"
+    for path in files:
+        sc = ptb.load_scene_file(_gltf_with_image(tmp_path, path.stem, path.read_bytes(), "image/" + path.suffix[1:]))
+        tex = sc.textures[0]
+        if path.name in refused:
+            assert tex.shape[0] == 0, path.name  # no texels: shaded with the reference's placeholder colour
+            continue
+        raw = gzip.decompress((idir / f"{path.stem}.raw.gz").read_bytes())
+        head, body = raw.split(b"\n", 1)
+        w, h, c = (int(x) for x in head.split())
+        assert c == 3
+        ref = np.frombuffer(body, np.uint8).reshape(h, w, 3)
+        if stb.exists():
+            out = tmp_path / "live.raw"
+            subprocess.run([str(stb), str(path), str(out), "3"], check=True)
+            assert out.read_bytes() == raw, path.name  # the fixture is what the reference's decoder says today
+        assert tex.shape == (h, w, 3), (path.name, tex.shape)
+        assert np.array_equal(tex, ref.astype(np.float32)), (path.name, int((tex != ref).sum()))
+
+
+def test_obj_material_texture_files_follow_the_references_binding(ptb, core_lib, tmp_path):
+    """An .mtl with map_Kd (a BMP) and map_Ke (a TGA): the reference loads every texture file with stbi_load(path, ..., 3) but binds
+    only assimp's BASE_COLOR and EMISSIVE types (src/HostScene.cpp:52-72,174-184) — for an OBJ that is map_Ke; map_Kd takes a slot in the
+    texture list and is bound to nothing.  A texture file that does not exist aborts the load, as there."""
+    import gzip, shutil
+    idir = GOLD / "images"
+    shutil.copy(idir / "bmp24_hdr40_33x17.bmp", tmp_path / "kd.bmp")
+    shutil.copy(idir / "tga24_rle_29x14.tga", tmp_path / "ke.tga")
+    (tmp_path / "m.mtl").write_text("newmtl glow\nKd 0.2 0.3 0.4\nKe 1 1 1\nmap_Kd -s 1 1 1 kd.bmp\nmap_Ke ke.tga\nnewmtl plain\nKd 0.5 0.5 0.5\n")
+    (tmp_path / "s.obj").write_text("mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nusemtl glow\nf 1/1 2/2 3/3\nusemtl plain\nf 1/1 3/3 4/4\n")
+    sc = ptb.load_scene_file(tmp_path / "s.obj")
+    assert len(sc.textures) == 2 and sc.textures[0].shape == (17, 33, 3) and sc.textures[1].shape == (14, 29, 3)
+    glow, plain = sc.mats[0], sc.mats[1]
+    assert int(glow["base_tex"]) == -1 and int(glow["emis_tex"]) == 1 and int(plain["base_tex"]) == -1 and int(plain["emis_tex"]) == -1
+    raw = gzip.decompress((idir / "tga24_rle_29x14.raw.gz").read_bytes()).split(b"\n", 1)[1]
+    assert np.array_equal(sc.textures[1], np.frombuffer(raw, np.uint8).reshape(14, 29, 3).astype(np.float32))
+    (tmp_path / "m.mtl").write_text("newmtl glow\nmap_Ke missing.png\n")
+    with pytest.raises(Exception, match="Cannot load texture data"):
+        ptb.load_scene_file(tmp_path / "s.obj")
