@@ -44,7 +44,7 @@ int main(int argc, char **argv) {
     if (argc < 7) {
         fprintf(stderr,
                 "usage: ref_cpu <scene.ptscene> <W> <H> <spp> <depth> <out.ppm|-> [--cam lx ly lz fx fy fz vfov hfov]\n"
-                "               [--yuv out.yuv] [--threads n] [--rect ox oy w h]\n");
+                "               [--yuv out.yuv] [--threads n] [--rect ox oy w h] [--row-stride k]\n");
         return 2;
     }
     const char *scene_path = argv[1];
@@ -56,11 +56,13 @@ int main(int argc, char **argv) {
     const char *yuv_path = nullptr;
     int threads = omp_get_max_threads();
     int rect[4] = {0, 0, W, H};
+    int row_stride = 1;  // > 1: only every k-th row of the rect is rendered (a uniform sample of the frame for timing)
     for (int i = 7; i < argc; i++) {
         if (!strcmp(argv[i], "--cam") && i + 8 < argc) { for (int k = 0; k < 8; k++) cam[k] = (float)atof(argv[i + 1 + k]); i += 8; }
         else if (!strcmp(argv[i], "--yuv") && i + 1 < argc) yuv_path = argv[++i];
         else if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--rect") && i + 4 < argc) { for (int k = 0; k < 4; k++) rect[k] = atoi(argv[i + 1 + k]); i += 4; }
+        else if (!strcmp(argv[i], "--row-stride") && i + 1 < argc) row_stride = atoi(argv[++i]) > 0 ? atoi(argv[i]) : 1;
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
 
@@ -118,6 +120,7 @@ int main(int argc, char **argv) {
     auto t0 = std::chrono::high_resolution_clock::now();
 #pragma omp parallel for schedule(dynamic, 1)
     for (int j = 0; j < rect[3]; j++) {
+        if (j % row_stride) continue;
         for (int i = 0; i < rect[2]; i++) {
             // --- body of `render`, src/DevicePathTracer.h:76-119 ---
             int x = rect[0] + i;
@@ -164,10 +167,10 @@ int main(int argc, char **argv) {
         FILE *f = fopen(yuv_path, "wb");
         if (f) { fwrite(fb_yuv.data(), 1, (size_t)W * (size_t)H * 3 / 2, f); fclose(f); }
     }
-    double samples = (double)rect[2] * (double)rect[3] * (double)spp;
+    double samples = (double)rect[2] * (double)((rect[3] + row_stride - 1) / row_stride) * (double)spp;
     printf("{\"impl\": \"ref_cpu\", \"seconds\": %.6f, \"bvh_build_seconds\": %.6f, \"samples\": %.0f, \"msamples_per_s\": %.6f, \"threads\": %d, "
-           "\"width\": %d, \"height\": %d, \"spp\": %d, \"depth\": %u, \"rect\": [%d, %d, %d, %d]}\n",
-           sec, bsec, samples, samples / sec / 1e6, threads, W, H, spp, depth, rect[0], rect[1], rect[2], rect[3]);
+           "\"width\": %d, \"height\": %d, \"spp\": %d, \"depth\": %u, \"rect\": [%d, %d, %d, %d], \"row_stride\": %d}\n",
+           sec, bsec, samples, samples / sec / 1e6, threads, W, H, spp, depth, rect[0], rect[1], rect[2], rect[3], row_stride);
     pts_free(&ps);
     return 0;
 }
