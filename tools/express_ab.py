@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Express lane for the longest chains of an N-GPU frame, emulated on one GPU (1080p cornell_duck, 1024 spp): every rank's share is rendered
 one after the other, either in ONE launch (baseline) or as an express launch — the first n_sms * warps blocks of the rank's list, one block
-per warp, on n_sms small CTAs — beside a main launch on the other SMs.   tools/express_ab.py [world] [spp] [n_sms:warps,...]"""
+per warp, on n_sms small CTAs — beside a main launch on the other SMs.   tools/express_ab.py [world] [spp] [n_sms:warps[:refill_at[:node_burst]],...]   (n_sms 0 = ONE launch with `warps` warps per SM, 0 = the core's rule)"""
 import json, sys
 from pathlib import Path
 import numpy as np
@@ -12,7 +12,7 @@ from ptb200 import sched  # noqa: E402
 
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 spp = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
-configs = [(0, 0)] + [tuple(int(x) for x in a.split(":")) for a in (sys.argv[3] if len(sys.argv) > 3 else "8:4,16:4,24:4,16:8").split(",")]
+configs = [(0, 0, 0, 2)] + [(tuple(int(x) for x in a.split(":")) + (0, 2))[:4] for a in (sys.argv[3] if len(sys.argv) > 3 else "8:4,16:4,24:4,16:8").split(",")]  # n_sms:warps[:refill_at[:node_burst]]
 w, h = 1920, 1080
 sms = torch.cuda.get_device_properties(0).multi_processor_count
 pt = ptb200.PathTracer(0)
@@ -28,7 +28,8 @@ order = sched.lpt_block_order(costs, bw, sched.lpt_levels(world))
 packed = ((order % bw) | ((order // bw) << 16)).to(torch.int32)
 torch.cuda.synchronize()
 ref = None
-for n_sms, warps in configs:
+for n_sms, warps, refill, burst in configs:
+    pt.set_option(ptb200.PT_OPT_REFILL_AT, refill); pt.set_option(ptb200.PT_OPT_NODE_BURST, burst)
     rgb.zero_()
     per_rank, express_ms = [], []
     for rank in range(world):
@@ -59,6 +60,6 @@ for n_sms, warps in configs:
     if ref is None:
         ref = img
     ms = max(per_rank)
-    print(json.dumps({"express_sms": n_sms, "express_warps_per_sm": warps, "world": world, "ms": ms, "msamples_per_s_whole_job": round(w * h * spp / ms / 1e3, 1),
+    print(json.dumps({"express_sms": n_sms, "express_warps_per_sm": warps, "refill_at": refill, "node_burst": burst, "world": world, "ms": ms, "msamples_per_s_whole_job": round(w * h * spp / ms / 1e3, 1),
                       "per_rank_ms": per_rank, "express_launch_ms": express_ms, "identical": bool(np.array_equal(img, ref))}), flush=True)
 pt.close()
