@@ -133,7 +133,7 @@ def flat_scene_file(tmpdir: Path) -> Path:
     return flat
 
 
-def cpu_reference_sample(threads: int, rect=None, spp=4, row_stride=6):
+def cpu_reference_sample(threads: int, rect=None, spp=4, row_stride=9):
     """Times the reference's CPU implementation (oracle/_ref/ref_cpu: its own headers host-compiled, OpenMP) on a bounded sample of the
     workload.  Default: every `row_stride`-th row of the WHOLE 1920x1080 frame at `spp` samples, depth 10 — a uniform sample of the frame's
     pixels, so Msamples/s of the sample is an unbiased estimate of the frame's (the centre rect used before is the most
