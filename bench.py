@@ -400,7 +400,9 @@ def main():
         torch.cuda.synchronize(device)
         pt.set_retire_log(0, 0)
         lg = log.view(n_log, 2)
-        used = lg[:, 1] > 0
+        # the pilot launch of the same frame logs too (and may run more warps than the render launch, whose entries then survive): a pilot
+        # warp ended before the render launch began, i.e. before the latest start in the log; a render warp ends after it
+        used = lg[:, 1] > lg[:, 0].max()
         if bool(used.any()):
             t0 = lg[used, 0].min()
             ends = ((lg[used, 1] - t0).double() / 1e6).sort().values
