@@ -108,6 +108,7 @@ inline bool decode_bmp(const unsigned char *bytes, size_t len, int &w, int &h, s
         }
     }
     const bool flip = img_y > 0;
+    if (img_y == INT32_MIN) { err = "Very large image (corrupt?)"; return false; }
     img_y = std::abs(img_y);
     if (img_x > kMaxDimension || img_y > kMaxDimension || img_x < 0) { err = "Very large image (corrupt?)"; return false; }
     int psize = 0;

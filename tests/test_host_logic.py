@@ -436,6 +436,21 @@ def test_bmp_and_tga_textures_decode_to_the_texels_of_the_references_own_decoder
             assert out.read_bytes() == raw, path.name  # the fixture is what the reference's decoder says today
         assert tex.shape == (h, w, 3), (path.name, tex.shape)
         assert np.array_equal(tex, ref.astype(np.float32)), (path.name, int((tex != ref).sum()))
+    # truncated and corrupted files never crash the loader: they decode (missing bytes read as zero, as in stb_image) or fall back to the placeholder
+    rng = np.random.default_rng(5)
+    for path in files[::3]:
+        data = path.read_bytes()
+        for cut in (0, 1, 10, 19, len(data) // 2, len(data) - 1):
+            sc = ptb.load_scene_file(_gltf_with_image(tmp_path, "cut", data[:cut] or b"\0", "image/" + path.suffix[1:]))
+            assert len(sc.textures) == 1
+        noisy = bytearray(data)
+        for k in rng.integers(0, min(len(noisy), 64), 6):
+            noisy[int(k)] = int(rng.integers(0, 256))
+        noisy[12:16] = b"\x10\x00\x10\x00" if path.suffix == ".tga" else noisy[12:16]  # keep a corrupted TGA small (16 x 16)
+        if path.suffix == ".bmp":
+            noisy[18:26] = (16).to_bytes(4, "little") + (16).to_bytes(4, "little")
+        sc = ptb.load_scene_file(_gltf_with_image(tmp_path, "noisy", bytes(noisy), "image/" + path.suffix[1:]))
+        assert len(sc.textures) == 1
 
 
 def test_obj_material_texture_files_follow_the_references_binding(ptb, core_lib, tmp_path):
