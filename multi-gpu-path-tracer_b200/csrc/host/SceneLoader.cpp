@@ -564,11 +564,31 @@ bool decode_png(const unsigned char *bytes, size_t n, int &width, int &height, i
         channels = samples + (add_alpha ? 1 : 0);
         out.resize((size_t)w * (size_t)h * (size_t)channels);
         int scale = depth < 8 ? 255 / ((1 << depth) - 1) : 1;
+        // colour-key transparency (tRNS on a grey or RGB image) as stb_image resolves it: the key's low byte scaled like the samples
+        // (16-bit images: the whole 16-bit key against the whole 16-bit samples); alpha 0 where every sample equals the key, else 255.
+        // The reference walks an embedded texture's buffer three bytes per texel whatever the channel count, so alpha bytes become texels.
+        int key[3] = {0, 0, 0};
+        if (add_alpha) {
+            if (trns.size() != (size_t)samples * 2) { err = "bad tRNS len"; return false; }
+            for (int s = 0; s < samples; s++) {
+                const int k16 = (trns[(size_t)s * 2] << 8) | trns[(size_t)s * 2 + 1];
+                key[s] = depth == 16 ? k16 : (((k16 & 255) * scale) & 255);
+            }
+        }
+        auto sample16 = [&](int x, int y, int s) -> int {
+            const unsigned char *row = img.data() + (size_t)y * full_rowbytes;
+            const size_t at = ((size_t)x * (size_t)samples + (size_t)s) * 2;
+            return (row[at] << 8) | row[at + 1];
+        };
         for (int y = 0; y < h; y++)
             for (int x = 0; x < w; x++) {
                 unsigned char *o = &out[((size_t)y * (size_t)w + (size_t)x) * (size_t)channels];
-                for (int s = 0; s < samples; s++) o[s] = (unsigned char)(sample(x, y, s) * scale);
-                if (add_alpha) o[samples] = 255;  // colour-key transparency is not resolved (unused downstream)
+                bool is_key = add_alpha;
+                for (int s = 0; s < samples; s++) {
+                    o[s] = (unsigned char)(sample(x, y, s) * scale);
+                    if (add_alpha) is_key = is_key && (depth == 16 ? sample16(x, y, s) : (int)o[s]) == key[s];
+                }
+                if (add_alpha) o[samples] = is_key ? 0 : 255;
             }
     }
     width = w;

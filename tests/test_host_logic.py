@@ -472,3 +472,32 @@ def test_obj_material_texture_files_follow_the_references_binding(ptb, core_lib,
     (tmp_path / "m.mtl").write_text("newmtl glow\nmap_Ke missing.png\n")
     with pytest.raises(Exception, match="Cannot load texture data"):
         ptb.load_scene_file(tmp_path / "s.obj")
+
+
+def test_png_textures_decode_to_the_texels_of_the_references_own_decoder(ptb, core_lib, tmp_path):
+    """tests/golden/png/*.png — written byte by byte (oracle/make_golden_png.py): every colour type and bit depth, a random filter type per
+    row, Adam7 interlacing, tRNS for palettes and as a colour key, split IDAT — with what the reference's decoder returns for an embedded
+    texture (stb_image, native channel count).  The reference then walks that buffer three bytes per texel WHATEVER the channel count
+    (src/HostScene.cpp:37-46: alpha and grey bytes become texels; with fewer than three channels it runs off the buffer — only the texels
+    that lie inside it are compared).  The repo's PNG reader must give the same bytes."""
+    import gzip
+    pdir = GOLD / "png"
+    files = sorted(pdir.glob("*.png"))
+    assert len(files) >= 26
+    stb = ROOT / "oracle" / "_ref" / "ref_stb"
+    channels_seen = set()
+    for path in files:
+        raw = gzip.decompress((pdir / f"{path.stem}.raw.gz").read_bytes())
+        head, body = raw.split(b"\n", 1)
+        w, h, c = (int(x) for x in head.split())
+        channels_seen.add(c)
+        if stb.exists():
+            out = tmp_path / "live.raw"
+            subprocess.run([str(stb), str(path), str(out)], check=True)
+            assert out.read_bytes() == raw, path.name
+        flat = np.frombuffer(body, np.uint8)
+        n_tex = min(w * h, len(flat) // 3)
+        tex = ptb.load_scene_file(_gltf_with_image(tmp_path, path.stem, path.read_bytes(), "image/png")).textures[0]
+        assert tex.shape == (h, w, 3), (path.name, tex.shape)
+        assert np.array_equal(tex.reshape(-1, 3)[:n_tex], flat[:n_tex * 3].reshape(n_tex, 3).astype(np.float32)), path.name
+    assert channels_seen == {1, 2, 3, 4}
