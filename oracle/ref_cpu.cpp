@@ -56,12 +56,14 @@ int main(int argc, char **argv) {
     const char *yuv_path = nullptr;
     int threads = omp_get_max_threads();
     int rect[4] = {0, 0, W, H};
+    int trace_x = -1, trace_y = -1;  // --trace-pixel x y: print what ray_color returns for every sample of that pixel (debugging the restatement)
     int row_stride = 1;  // > 1: only every k-th row of the rect is rendered (a uniform sample of the frame for timing)
     for (int i = 7; i < argc; i++) {
         if (!strcmp(argv[i], "--cam") && i + 8 < argc) { for (int k = 0; k < 8; k++) cam[k] = (float)atof(argv[i + 1 + k]); i += 8; }
         else if (!strcmp(argv[i], "--yuv") && i + 1 < argc) yuv_path = argv[++i];
         else if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--rect") && i + 4 < argc) { for (int k = 0; k < 4; k++) rect[k] = atoi(argv[i + 1 + k]); i += 4; }
+        else if (!strcmp(argv[i], "--trace-pixel") && i + 2 < argc) { trace_x = atoi(argv[i + 1]); trace_y = atoi(argv[i + 2]); i += 2; }
         else if (!strcmp(argv[i], "--row-stride") && i + 1 < argc) row_stride = atoi(argv[++i]) > 0 ? atoi(argv[i]) : 1;
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
@@ -134,7 +136,9 @@ int main(int argc, char **argv) {
                 float u = float(x + curand_uniform(&local_rand_state)) / float(res.width);
                 float v = float(y + curand_uniform(&local_rand_state)) / float(res.height);
                 ray r = cam_obj->get_ray(u, v);
-                col += cam_obj->ray_color(r, &world, cc, depth, &lights, &local_rand_state);
+                const float3 one = cam_obj->ray_color(r, &world, cc, depth, &lights, &local_rand_state);
+                if (x == trace_x && y == trace_y) fprintf(stderr, "TRACE sample %d colour %.9g %.9g %.9g\n", s, one.x, one.y, one.z);
+                col += one;
             }
             float3 color_modifier = make_float3(1, 1, 1);
             int3 color = make_int3(255.99 * col / float(spp) * color_modifier);

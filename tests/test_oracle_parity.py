@@ -74,3 +74,25 @@ def test_reference_cuda_and_host_builds_differ_by_the_stated_tolerance():
         assert frac1 < 1.0 or m["depth"] <= 3, name  # they do differ: bit-exactness across builds is not a property of the reference
         n += 1
     assert n >= 3
+
+
+RANDOM = json.loads((GOLD / "random" / "cases.json").read_text()) if (GOLD / "random" / "cases.json").exists() else {}
+
+
+@pytest.mark.parametrize("name", sorted(RANDOM) or ["<no fixtures>"])
+def test_oracle_matches_host_compiled_reference_on_random_scenes(oracle, ptb, name):
+    """tests/golden/random: whole images the reference's own headers (oracle/_ref/ref_cpu) rendered of random scenes — triangle soups, a tilted
+    floor and wall, several universal materials with emitters, textures bound as base-colour and emissive maps, random cameras / sizes / spp /
+    depths (oracle/make_golden_random.py; tools/fuzz_oracle.py runs 240 more such cases against the live binary: 0 differ).  Bit-exact, RGB
+    and I420: the restatement is the reference's arithmetic on geometry and materials the cornell_duck fixtures do not have."""
+    if not RANDOM:
+        pytest.skip("tests/golden/random not generated")
+    m = RANDOM[name]
+    sc = ptb.load_scene_file(GOLD / "random" / f"{name}.ptscene.gz")
+    assert len(sc.tri_mat) == m["triangles"] and len(sc.mats) == m["materials"] and len(sc.textures) == m["textures"]
+    cam = dict(look_from=tuple(m["camera"]["look_from"]), front=tuple(m["camera"]["front"]), vfov=m["camera"]["vfov"], hfov=m["camera"]["hfov"])
+    rgb, yuv, _ = oracle.render(sc, m["width"], m["height"], m["spp"], m["depth"], camera=cam)
+    ref = np.array(Image.open(GOLD / "random" / f"{name}.png").convert("RGB"))
+    assert np.array_equal(rgb, ref), f"{(np.abs(ref.astype(int) - rgb.astype(int)).max(axis=2) > 0).sum()} pixels differ"
+    assert np.array_equal(yuv, np.frombuffer(gzip.decompress((GOLD / "random" / f"{name}.yuv.gz").read_bytes()), np.uint8))
+    assert int((ref.max(axis=2) > 0).sum()) == m["lit_pixels"] > 0
