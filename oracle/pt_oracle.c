@@ -104,11 +104,18 @@ static v3 random_cosine_direction(rng_ctx *c) {
 }
 pto_vec3 pto_random_cosine_direction(pto_rng *s) { rng_ctx c = {s, NULL, NULL, 0, 0, 0.f}; return random_cosine_direction(&c); }
 
+/* make_random_float3 draws its three components inside ONE argument list (helper_math.h:1505-1507): the order is unspecified in C++.  nvcc's
+ * device code evaluates left to right (x, y, z: what the CUDA core and this restatement do), g++ on x86-64 right to left.  The switch exists
+ * so that the HOST build of the reference's dead classes (oracle/_ref/ref_cpu_spheres) can pin everything else of rows D1-D6 bit for bit. */
+static int g_triple_zyx = 0;
+void pto_set_triple_draw_order_zyx(int on) { g_triple_zyx = on; }
 static v3 random_in_unit_sphere(rng_ctx *c) {
     /* helper_math.h:1504-1518; draw order x,y,z (builder-defined, see header comment) */
     v3 p;
     do {
-        float a = U(c), b = U(c), d = U(c);
+        float a, b, d;
+        if (g_triple_zyx) { d = U(c); b = U(c); a = U(c); }
+        else { a = U(c); b = U(c); d = U(c); }
         p = vsub(vscale(V(a, b, d), 2.0f), V(1.0f, 1.0f, 1.0f));
     } while (vdot(p, p) >= 1.0f);
     return p;

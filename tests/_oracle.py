@@ -85,6 +85,10 @@ class Oracle:
         w = self.lib.pto_world_create(C.byref(d))
         return w
 
+    def set_triple_draw_order_zyx(self, on):
+        """Test only: the argument-evaluation order of the HOST build of the reference (see pt_oracle.c)."""
+        self.lib.pto_set_triple_draw_order_zyx(int(bool(on)))
+
     def render(self, scene_or_world, width, height, spp, depth, camera=None, rect=None, threads=0, want_accum=False, keyed_chunks=0):
         """Returns (rgb[h,w,3] u8, yuv[w*h*3/2] u8, stats dict[, accum]).  keyed_chunks > 0: the (pixel, sample)-keyed RNG mode."""
         self.lib.pto_set_keyed_chunks(keyed_chunks)
