@@ -52,6 +52,11 @@ struct JVal {
         return nullptr;
     }
     bool has(const char *key) const { return get(key) != nullptr; }
+    const JVal &need(const char *key) const {  // a required member: a malformed file raises, it never dereferences null
+        const JVal *v = get(key);
+        if (!v) throw std::runtime_error(std::string("glTF: missing \"") + key + "\"");
+        return *v;
+    }
     size_t size() const { return kind == Arr ? arr.size() : 0; }
     const JVal &at(size_t i) const {
         if (kind != Arr || i >= arr.size()) throw std::runtime_error("glTF: array index out of range");
@@ -224,9 +229,9 @@ struct Gltf {
     View bufferView(int idx) const {
         const JVal &bv = top("bufferViews").at((size_t)idx);
         int b = bv.get("buffer") ? bv.get("buffer")->integer(0) : 0;
-        size_t off = bv.get("byteOffset") ? (size_t)bv.get("byteOffset")->number(0) : 0;
-        size_t len = bv.get("byteLength") ? (size_t)bv.get("byteLength")->number(0) : 0;
-        size_t stride = bv.get("byteStride") ? (size_t)bv.get("byteStride")->number(0) : 0;
+        size_t off = sizeFrom(bv.get("byteOffset"), "byteOffset");
+        size_t len = sizeFrom(bv.get("byteLength"), "byteLength");
+        size_t stride = sizeFrom(bv.get("byteStride"), "byteStride");
         if (b < 0 || (size_t)b >= buffers.size() || off + len > buffers[(size_t)b].size())
             throw std::runtime_error("glTF: bufferView out of range");
         return {buffers[(size_t)b].data() + off, len, stride};
@@ -248,21 +253,35 @@ struct Gltf {
         throw std::runtime_error("glTF: unsupported accessor type " + t);
     }
 
+    // sizes out of the JSON: a negative, absurd or non-numeric value raises instead of being cast
+    static size_t sizeFrom(const JVal *v, const char *what) {
+        const double d = v ? v->number(-1) : 0.0;
+        if (!(d >= 0.0) || d > 1e15) throw std::runtime_error(std::string("glTF: bad ") + what);
+        return (size_t)d;
+    }
+    static size_t countOf(const JVal &acc) { return sizeFrom(&acc.need("count"), "accessor count"); }
+    static size_t offsetOf(const JVal &acc) { return sizeFrom(acc.get("byteOffset"), "byteOffset"); }
+
     // Reads accessor `idx` as floats (normalised integers are scaled) with `want` comps.
     std::vector<float> readFloats(int idx, int want) const {
         const JVal &acc = top("accessors").at((size_t)idx);
         if (acc.has("sparse")) throw std::runtime_error("glTF: sparse accessors unsupported");
-        int ct = acc.get("componentType")->integer(0);
-        int n = typeCount(acc.get("type")->str);
-        size_t count = (size_t)acc.get("count")->number(0);
+        int ct = acc.need("componentType").integer(0);
+        int n = typeCount(acc.need("type").str);
+        size_t count = countOf(acc);
         bool normalized = acc.get("normalized") && acc.get("normalized")->b;
-        std::vector<float> out(count * (size_t)want, 0.f);
-        if (!acc.has("bufferView")) return out;
-        View v = bufferView(acc.get("bufferView")->integer(0));
-        size_t aoff = acc.get("byteOffset") ? (size_t)acc.get("byteOffset")->number(0) : 0;
+        if (!acc.has("bufferView")) {
+            if (count > (1u << 28)) throw std::runtime_error("glTF: bad accessor count");
+            return std::vector<float>(count * (size_t)want, 0.f);
+        }
+        View v = bufferView(acc.need("bufferView").integer(0));
+        size_t aoff = offsetOf(acc);
         size_t cs = (size_t)compSize(ct);
         size_t stride = v.stride ? v.stride : cs * (size_t)n;
-        if (count && aoff + (count - 1) * stride + cs * (size_t)n > v.len) throw std::runtime_error("glTF: accessor overruns bufferView");
+        // count, stride and offset are each bounded by the view's length first, so the exact test below cannot wrap around
+        if (count > v.len || aoff > v.len || (count > 1 && stride > v.len) || (count && aoff + (count - 1) * stride + cs * (size_t)n > v.len))
+            throw std::runtime_error("glTF: accessor overruns bufferView");
+        std::vector<float> out(count * (size_t)want, 0.f);
         for (size_t i = 0; i < count; i++) {
             const unsigned char *e = v.ptr + aoff + i * stride;
             for (int c = 0; c < std::min(n, want); c++) {
@@ -284,13 +303,14 @@ struct Gltf {
     }
     std::vector<uint32_t> readIndices(int idx) const {
         const JVal &acc = top("accessors").at((size_t)idx);
-        int ct = acc.get("componentType")->integer(0);
-        size_t count = (size_t)acc.get("count")->number(0);
-        View v = bufferView(acc.get("bufferView")->integer(0));
-        size_t aoff = acc.get("byteOffset") ? (size_t)acc.get("byteOffset")->number(0) : 0;
+        int ct = acc.need("componentType").integer(0);
+        size_t count = countOf(acc);
+        View v = bufferView(acc.need("bufferView").integer(0));
+        size_t aoff = offsetOf(acc);
         size_t cs = (size_t)compSize(ct);
         size_t stride = v.stride ? v.stride : cs;
-        if (count && aoff + (count - 1) * stride + cs > v.len) throw std::runtime_error("glTF: index accessor overruns bufferView");
+        if (count > v.len || aoff > v.len || (count > 1 && stride > v.len) || (count && aoff + (count - 1) * stride + cs > v.len))
+            throw std::runtime_error("glTF: index accessor overruns bufferView");
         std::vector<uint32_t> out(count);
         for (size_t i = 0; i < count; i++) {
             const unsigned char *q = v.ptr + aoff + i * stride;
@@ -666,7 +686,7 @@ HostScene SceneLoader::loadGLTF(const std::string &path, bool binary) {
     std::map<int, int> imageToTex;
     auto textureForSlot = [&](const JVal *slot) -> std::optional<int> {
         if (!slot || !slot->get("index")) return std::nullopt;
-        int ti = slot->get("index")->integer(-1);
+        int ti = slot->need("index").integer(-1);
         const JVal &textures = g.top("textures");
         if (ti < 0 || (size_t)ti >= textures.size()) return std::nullopt;
         const JVal *src = textures.at((size_t)ti).get("source");
@@ -775,10 +795,11 @@ HostScene SceneLoader::loadGLTF(const std::string &path, bool binary) {
                 if (mode != 4 && mode != 5 && mode != 6) continue;  // points/lines are removed (SortByPType)
                 const JVal *attrs = prim.get("attributes");
                 if (!attrs || !attrs->get("POSITION")) continue;
-                std::vector<float> pos = g.readFloats(attrs->get("POSITION")->integer(0), 3);
+                std::vector<float> pos = g.readFloats(attrs->need("POSITION").integer(0), 3);
                 std::vector<float> uv;
                 if (attrs->get("TEXCOORD_0")) uv = g.readFloats(attrs->get("TEXCOORD_0")->integer(0), 2);
                 size_t nv = pos.size() / 3;
+                if (!uv.empty() && uv.size() < nv * 2) throw std::runtime_error("glTF: TEXCOORD_0 has fewer elements than POSITION");
                 std::vector<uint32_t> idx;
                 if (prim.get("indices")) idx = g.readIndices(prim.get("indices")->integer(0));
                 else {

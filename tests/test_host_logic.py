@@ -501,3 +501,56 @@ def test_png_textures_decode_to_the_texels_of_the_references_own_decoder(ptb, co
         assert tex.shape == (h, w, 3), (path.name, tex.shape)
         assert np.array_equal(tex.reshape(-1, 3)[:n_tex], flat[:n_tex * 3].reshape(n_tex, 3).astype(np.float32)), path.name
     assert channels_seen == {1, 2, 3, 4}
+
+
+def test_malformed_gltf_raises_and_never_crashes(ptb, core_lib, tmp_path):
+    """Found by tools/fuzz_loader.py (byte mutations of the reference's models, each load in a child process): accessors without
+    `componentType` / `type` / `count`, texture slots without `index`, negative or absurd counts, offsets and strides, TEXCOORD_0 shorter than
+    POSITION.  Every one raises; none dereferences a missing member or wraps a size around."""
+    import base64, copy
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32).tobytes() + bytes([0, 1, 2, 0])
+    good = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+            "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "TEXCOORD_0": 1}, "indices": 2, "material": 0}]}],
+            "materials": [{"name": "m", "emissiveFactor": [1, 1, 1], "pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}}],
+            "textures": [{"source": 0}], "images": [{"uri": "data:image/png;base64,"}],
+            "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}, {"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC2"},
+                          {"bufferView": 1, "componentType": 5121, "count": 3, "type": "SCALAR"}],
+            "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 4}],
+            "buffers": [{"byteLength": 40, "uri": "data:application/octet-stream;base64," + base64.b64encode(tri).decode()}]}
+
+    def load(mutate):
+        g = copy.deepcopy(good)
+        mutate(g)
+        path = tmp_path / "m.gltf"
+        path.write_text(json.dumps(g))
+        return ptb.load_scene_file(path)
+
+    def drop(path_keys):
+        def f(g):
+            o = g
+            for k in path_keys[:-1]:
+                o = o[k]
+            del o[path_keys[-1]]
+        return f
+
+    def put(path_keys, value):
+        def f(g):
+            o = g
+            for k in path_keys[:-1]:
+                o = o[k]
+            o[path_keys[-1]] = value
+        return f
+    bad = [drop(["accessors", 0, "componentType"]), drop(["accessors", 0, "type"]), drop(["accessors", 0, "count"]), drop(["accessors", 2, "componentType"]),
+           drop(["accessors", 2, "count"]), drop(["accessors", 2, "bufferView"]),
+           put(["accessors", 0, "count"], -1), put(["accessors", 0, "count"], 1e30), put(["accessors", 0, "count"], 2 ** 61), put(["accessors", 2, "count"], 2 ** 62),
+           put(["accessors", 0, "byteOffset"], -4), put(["accessors", 0, "byteOffset"], 2 ** 63), put(["bufferViews", 0, "byteStride"], 2 ** 62),
+           put(["bufferViews", 0, "byteLength"], -36), put(["bufferViews", 0, "byteOffset"], 1e18), put(["bufferViews", 0, "buffer"], 7),
+           put(["accessors", 1, "count"], 2), put(["accessors", 0, "componentType"], 1234), put(["accessors", 0, "type"], "MAT9"), put(["accessors", 2, "count"], "three")]
+    for k, m in enumerate(bad):
+        with pytest.raises(Exception):
+            load(m)
+    # (the unmutated file is fine apart from its empty image: that one loads with a placeholder texture)
+    sc = load(lambda g: None)
+    assert len(sc.tri_mat) == 1 and len(sc.textures) == 1
+    sc = load(drop(["materials", 0, "pbrMetallicRoughness", "baseColorTexture", "index"]))  # a slot without an index is no texture
+    assert len(sc.tri_mat) == 1 and len(sc.textures) == 0
