@@ -179,6 +179,7 @@ private:
         n_comp_ = get8();
         if (n_comp_ != 1 && n_comp_ != 3 && n_comp_ != 4) return fail(err, "bad component count");
         if (Lf != 8 + 3 * n_comp_) return fail(err, "bad SOF length");
+        if ((uint64_t)img_x_ * (uint64_t)img_y_ * (uint64_t)n_comp_ > 0x7fffffffull) return fail(err, "too large");  // stb_image's 2 GB limit
         rgb_ids_ = 0;
         h_max_ = v_max_ = 1;
         for (int i = 0; i < n_comp_; i++) {

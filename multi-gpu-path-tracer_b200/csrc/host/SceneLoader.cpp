@@ -496,6 +496,8 @@ bool decode_png(const unsigned char *bytes, size_t n, int &width, int &height, i
         pos += 12 + (size_t)len;
     }
     if (!have_ihdr || w <= 0 || h <= 0) { err = "missing IHDR"; return false; }
+    // stb_image's limits (STBI_MAX_DIMENSIONS and a 2 GB image): a corrupted header must not become a 50 GB allocation
+    if (w > (1 << 24) || h > (1 << 24) || (uint64_t)w * (uint64_t)h * 8u > 0x7fffffffull) { err = "Very large image (corrupt?)"; return false; }
     int samples;
     switch (ctype) {
         case 0: samples = 1; break;

@@ -451,6 +451,16 @@ def test_bmp_and_tga_textures_decode_to_the_texels_of_the_references_own_decoder
             noisy[18:26] = (16).to_bytes(4, "little") + (16).to_bytes(4, "little")
         sc = ptb.load_scene_file(_gltf_with_image(tmp_path, "noisy", bytes(noisy), "image/" + path.suffix[1:]))
         assert len(sc.textures) == 1
+    # a corrupted header that announces a gigantic image is refused at once (stb_image's limits), not allocated: PNG raises like the reference
+    # ("Cannot load texture data"), JPEG falls back to the placeholder
+    png = bytearray((GOLD / "png" / "type_0_depth_8_interlace_false_37x27.png").read_bytes())
+    png[16:20] = bytes([0x6D, 0, 0, 0x25])  # width 1 828 716 581
+    with pytest.raises(Exception, match="Very large image"):
+        ptb.load_scene_file(_gltf_with_image(tmp_path, "huge", bytes(png), "image/png"))
+    jpg = bytearray((GOLD / "jpeg" / "c444_q90_33x21.jpg").read_bytes())
+    sof = jpg.find(bytes([0xFF, 0xC0]))
+    jpg[sof + 5:sof + 9] = bytes([0xFF, 0xFF, 0xFF, 0xFF])  # 65535 x 65535
+    assert ptb.load_scene_file(_gltf_with_image(tmp_path, "hugej", bytes(jpg), "image/jpeg")).textures[0].shape[0] == 0
 
 
 def test_obj_material_texture_files_follow_the_references_binding(ptb, core_lib, tmp_path):
