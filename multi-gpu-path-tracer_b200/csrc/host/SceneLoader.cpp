@@ -1033,11 +1033,20 @@ HostScene read_ptscene(const std::string &path) {
     PtsHeader h;
     take(&h, sizeof h);
     if (memcmp(h.magic, "PTSC", 4) != 0 || h.version != 1) throw std::runtime_error("not a ptscene v1 file: " + path);
+    // the counts are checked against the bytes that are really there BEFORE anything is allocated (a corrupted header must raise, not reserve
+    // 100 GB), and every index against the table it points into
+    const uint64_t fixed = (uint64_t)h.n_tris * sizeof(PtsTri) + (uint64_t)h.n_spheres * sizeof(PtsSphere) + (uint64_t)h.n_mats * sizeof(PtsMat) + (uint64_t)h.n_tex * 8u;
+    if (fixed > buf.size() - pos) throw std::runtime_error("ptscene truncated (or its header is corrupt): " + path);
+    auto checkIndex = [&](int32_t idx, uint32_t n, bool optional, const char *what) {
+        if ((optional && idx < 0) || (idx >= 0 && (uint32_t)idx < n)) return;
+        throw std::runtime_error(std::string("ptscene: ") + what + " index out of range: " + path);
+    };
     HostScene s;
     s.triangles.resize(h.n_tris);
     for (auto &t : s.triangles) {
         PtsTri r;
         take(&r, sizeof r);
+        checkIndex(r.mat, h.n_mats, false, "triangle material");
         Vertex *v[3] = {&t.v0, &t.v1, &t.v2};
         for (int k = 0; k < 3; k++) {
             v[k]->position = make_float3(r.pos[3 * k], r.pos[3 * k + 1], r.pos[3 * k + 2]);
@@ -1050,6 +1059,7 @@ HostScene read_ptscene(const std::string &path) {
     for (auto &sp : s.spheres) {
         PtsSphere r;
         take(&r, sizeof r);
+        checkIndex(r.mat, h.n_mats, false, "sphere material");
         sp.center = make_float3(r.c[0], r.c[1], r.c[2]);
         sp.radius = r.r;
         sp.materialIdx = r.mat;
@@ -1058,6 +1068,9 @@ HostScene read_ptscene(const std::string &path) {
     for (auto &m : s.materials) {
         PtsMat r;
         take(&r, sizeof r);
+        if (r.type < 0 || r.type > 4) throw std::runtime_error("ptscene: unknown material type: " + path);
+        checkIndex(r.base_tex, h.n_tex, true, "base-colour texture");
+        checkIndex(r.emis_tex, h.n_tex, true, "emissive texture");
         m.type = (material_type)r.type;
         m.baseColor = make_float3(r.base[0], r.base[1], r.base[2]);
         m.emissiveFactor = make_float3(r.emis[0], r.emis[1], r.emis[2]);
@@ -1070,7 +1083,7 @@ HostScene read_ptscene(const std::string &path) {
     for (auto &t : s.textures) {
         int32_t wh[2];
         take(wh, sizeof wh);
-        if (wh[0] < 0 || wh[1] < 0) throw std::runtime_error("ptscene: bad texture size");
+        if (wh[0] < 0 || wh[1] < 0 || (uint64_t)wh[0] * (uint64_t)wh[1] * 3u > buf.size() - pos) throw std::runtime_error("ptscene: bad texture size: " + path);
         t.width = wh[0];
         t.height = wh[1];
         std::vector<unsigned char> px((size_t)t.width * (size_t)t.height * 3);
