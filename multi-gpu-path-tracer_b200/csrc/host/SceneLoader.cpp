@@ -73,7 +73,15 @@ struct JParser {
     void ws() {
         while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
     }
+    int depth = 0;  // nesting of the value being parsed: bounded, so that a file of 100 000 '[' raises instead of overflowing the stack
+    struct Nest {
+        int &d;
+        explicit Nest(int &dd) : d(dd) { ++d; }
+        ~Nest() { --d; }
+    };
     JPtr parse() {
+        Nest nest(depth);
+        if (depth > 256) fail("nesting too deep");
         ws();
         if (p >= end) fail("unexpected end");
         auto v = std::make_shared<JVal>();
@@ -764,7 +772,8 @@ HostScene SceneLoader::loadGLTF(const std::string &path, bool binary) {
     for (auto it = roots.rbegin(); it != roots.rend(); ++it) stack.push_back({*it, Mat4::identity()});
     size_t guard = 0;
     while (!stack.empty()) {
-        if (++guard > 10000000) throw std::runtime_error("glTF: node graph too deep / cyclic");
+        // a glTF node graph is a forest (every node has at most one parent): more visits than nodes means a cycle or a shared subtree
+        if (++guard > nodes.size() * 4 + 64) throw std::runtime_error("glTF: node graph is cyclic (or shares subtrees)");
         Frame fr = stack.back();
         stack.pop_back();
         const JVal &node = nodes.at((size_t)fr.node);

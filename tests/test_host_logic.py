@@ -556,9 +556,14 @@ def test_malformed_gltf_raises_and_never_crashes(ptb, core_lib, tmp_path):
            put(["accessors", 0, "byteOffset"], -4), put(["accessors", 0, "byteOffset"], 2 ** 63), put(["bufferViews", 0, "byteStride"], 2 ** 62),
            put(["bufferViews", 0, "byteLength"], -36), put(["bufferViews", 0, "byteOffset"], 1e18), put(["bufferViews", 0, "buffer"], 7),
            put(["accessors", 1, "count"], 2), put(["accessors", 0, "componentType"], 1234), put(["accessors", 0, "type"], "MAT9"), put(["accessors", 2, "count"], "three")]
+    bad.append(put(["nodes", 0, "children"], [0]))  # a node that is its own child
     for k, m in enumerate(bad):
         with pytest.raises(Exception):
             load(m)
+    deep = tmp_path / "deep.gltf"
+    deep.write_text('{"asset": ' + "[" * 100000 + "]" * 100000 + "}")  # 100 000 nested arrays: a parse error, not a stack overflow
+    with pytest.raises(Exception, match="nesting too deep"):
+        ptb.load_scene_file(deep)
     # (the unmutated file is fine apart from its empty image: that one loads with a placeholder texture)
     sc = load(lambda g: None)
     assert len(sc.tri_mat) == 1 and len(sc.textures) == 1
