@@ -599,3 +599,17 @@ def test_corrupt_ptscene_files_raise_before_anything_is_allocated(ptb, core_lib,
     for data in bad:
         r = run(data)
         assert r.returncode not in (0, -11, -6) and "ptscene" in (r.stderr + r.stdout), (r.returncode, (r.stderr + r.stdout)[-200:])
+
+
+def test_the_abi_header_is_plain_c(tmp_path):
+    """include/ptcore.h is the drop-in boundary: it must compile as C99 (pedantic) and as C++11 with nothing but itself — no torch, CUDA or
+    STL type in any signature."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "ptcore.h"\nint main(void) { PtCamera c; PtStats s; (void)c; (void)s; return ptcore_last_error(0) == 0; }\n')
+    inc = str(ROOT / "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + inc, "-fsyntax-only", str(src)], check=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-I" + inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
+    import re
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "ptcore.h").read_text(), flags=re.S)  # declarations only, comments removed
+    for banned in ("#include <cuda", "torch", "std::", "cudaStream_t", "at::"):
+        assert banned not in text, banned
