@@ -1,4 +1,4 @@
-// BmpTgaDecoder.h — BMP and TGA textures -> RGB8, with the texels the reference gets.
+// BmpTgaDecoder.h — BMP, TGA, GIF and PNM textures -> RGB8, with the texels the reference gets.
 //
 // The reference reads texture FILES with stbi_load(path, &w, &h, &n, 3) (src/HostScene.cpp:29), i.e. through the vendored
 // third-party/stb_image.h (v2.30) with three requested channels.  glTF itself only carries PNG / JPEG, so BMP and TGA reach the
@@ -325,6 +325,209 @@ inline bool decode_tga(const unsigned char *bytes, size_t len, int &w, int &h, s
     }
     w = width;
     h = height;
+    return true;
+}
+
+// ---- GIF (first frame) and binary PNM, the way stb_image returns them for three requested channels ------------------------------------------
+//   GIF  87a / 89a, first image only; pixels the frame does not draw stay (0,0,0) unless the screen's background index is > 0, in which case
+//        they get that palette entry — copied as stored, i.e. with red and blue exchanged (stb_image's palette is B,G,R,A and the copy is raw);
+//        a transparent index (graphic control extension) is "drawn" as nothing; interlaced rows in 8-8-4-2 order; LZW with at most 4096
+//        codes of <= 12 bits, deferred clear codes allowed, a stream that does not start with a clear code refused;
+//   PNM  P5 / P6 only, no comments inside numbers, one whitespace byte before the samples, maxval NOT used for scaling; 16-bit samples
+//        (maxval > 255) lose their HIGH byte: stb_image reads big-endian pairs into native (little-endian) words and keeps `>> 8`.
+inline bool is_gif(const unsigned char *b, size_t n) {
+    return n >= 6 && b[0] == 'G' && b[1] == 'I' && b[2] == 'F' && b[3] == '8' && (b[4] == '7' || b[4] == '9') && b[5] == 'a';
+}
+
+inline bool decode_gif(const unsigned char *bytes, size_t len, int &w, int &h, std::vector<unsigned char> &rgb, std::string &err) {
+    Reader s(bytes, len);
+    if (!is_gif(bytes, len)) { err = "Corrupt GIF"; return false; }
+    s.skip(6);
+    const int W = s.u16(), H = s.u16();
+    const int flags = s.u8(), bgindex = s.u8();
+    s.u8();  // aspect ratio
+    if ((uint64_t)W * (uint64_t)H * 4u > 0x7fffffffull) { err = "GIF image is too large"; return false; }
+    unsigned char pal[256][4] = {}, lpal[256][4] = {};  // stored B, G, R, A
+    auto read_table = [&](unsigned char (*t)[4], int n, int transp) {
+        for (int i = 0; i < n; i++) {
+            t[i][2] = (unsigned char)s.u8();
+            t[i][1] = (unsigned char)s.u8();
+            t[i][0] = (unsigned char)s.u8();
+            t[i][3] = transp == i ? 0 : 255;
+        }
+    };
+    if (flags & 0x80) read_table(pal, 2 << (flags & 7), -1);
+    const size_t pcount = (size_t)W * (size_t)H;
+    std::vector<unsigned char> out(pcount * 4, 0), history(pcount, 0);
+    int transparent = -1, eflags = 0;
+    for (;;) {
+        if (s.pos >= s.n + 16) { err = "Corrupt GIF"; return false; }  // reads past the end yield zeros = an unknown block code soon enough
+        const int tag = s.u8();
+        if (tag == 0x2C) {
+            const int x = s.u16(), y = s.u16(), iw = s.u16(), ih = s.u16();
+            if (x + iw > W || y + ih > H) { err = "Corrupt GIF"; return false; }
+            const long line = (long)W * 4;
+            const long start_x = (long)x * 4, start_y = (long)y * line, max_x = start_x + (long)iw * 4, max_y = start_y + (long)ih * line;
+            long cur_x = start_x, cur_y = iw == 0 ? max_y : start_y, step;
+            int parse;
+            const int lflags = s.u8();
+            if (lflags & 0x40) { step = 8 * line; parse = 3; } else { step = line; parse = 0; }
+            const unsigned char (*table)[4];
+            if (lflags & 0x80) { read_table(lpal, 2 << (lflags & 7), (eflags & 1) ? transparent : -1); table = lpal; }
+            else if (flags & 0x80) table = pal;
+            else { err = "Corrupt GIF"; return false; }
+            // LZW raster
+            const int lzw_cs = s.u8();
+            if (lzw_cs > 12) { err = "Corrupt GIF"; return false; }
+            struct Code { int16_t prefix; unsigned char first, suffix; };
+            std::vector<Code> codes(8192);
+            const int clear = 1 << lzw_cs;
+            for (int i = 0; i < clear; i++) codes[(size_t)i] = {(int16_t)-1, (unsigned char)i, (unsigned char)i};
+            bool first = true;
+            int codesize = lzw_cs + 1, codemask = (1 << codesize) - 1, avail = clear + 2, oldcode = -1, valid_bits = 0, blk = 0;
+            int32_t bits = 0;
+            std::vector<uint16_t> chain;
+            auto emit = [&](int code) {  // the code's string, first symbol first
+                chain.clear();
+                for (int c = code; c >= 0; c = codes[(size_t)c].prefix) {
+                    chain.push_back((uint16_t)c);
+                    if (chain.size() > 8192) break;
+                }
+                for (size_t k = chain.size(); k-- > 0;) {
+                    if (cur_y >= max_y) continue;
+                    const long idx = cur_x + cur_y;
+                    history[(size_t)(idx / 4)] = 1;
+                    const unsigned char *c = table[codes[chain[k]].suffix];
+                    if (c[3] > 128) {
+                        out[(size_t)idx] = c[2]; out[(size_t)idx + 1] = c[1]; out[(size_t)idx + 2] = c[0]; out[(size_t)idx + 3] = c[3];
+                    }
+                    cur_x += 4;
+                    if (cur_x >= max_x) {
+                        cur_x = start_x;
+                        cur_y += step;
+                        while (cur_y >= max_y && parse > 0) {
+                            step = (1L << parse) * line;
+                            cur_y = start_y + (step >> 1);
+                            --parse;
+                        }
+                    }
+                }
+            };
+            bool done = false;
+            while (!done) {
+                if (valid_bits < codesize) {
+                    if (blk == 0) {
+                        blk = s.u8();
+                        if (blk == 0) break;  // block terminator: the raster ends here
+                    }
+                    --blk;
+                    bits |= (int32_t)s.u8() << valid_bits;
+                    valid_bits += 8;
+                    if (s.pos > s.n + 1024) { err = "Corrupt GIF"; return false; }
+                } else {
+                    const int code = bits & codemask;
+                    bits >>= codesize;
+                    valid_bits -= codesize;
+                    if (code == clear) {
+                        codesize = lzw_cs + 1; codemask = (1 << codesize) - 1; avail = clear + 2; oldcode = -1; first = false;
+                    } else if (code == clear + 1) {
+                        s.skip(blk);
+                        while ((blk = s.u8()) > 0) { s.skip(blk); if (s.pos > s.n + 1024) break; }
+                        done = true;
+                    } else if (code <= avail) {
+                        if (first) { err = "Corrupt GIF"; return false; }
+                        if (oldcode >= 0) {
+                            Code &p = codes[(size_t)avail++];
+                            if (avail > 8192) { err = "Corrupt GIF"; return false; }
+                            p.prefix = (int16_t)oldcode;
+                            p.first = codes[(size_t)oldcode].first;
+                            p.suffix = (code == avail) ? p.first : codes[(size_t)code].first;
+                        } else if (code == avail) { err = "Corrupt GIF"; return false; }
+                        emit(code);
+                        if ((avail & codemask) == 0 && avail <= 0x0FFF) { codesize++; codemask = (1 << codesize) - 1; }
+                        oldcode = code;
+                    } else { err = "Corrupt GIF"; return false; }
+                }
+            }
+            if (bgindex > 0)
+                for (size_t pi = 0; pi < pcount; pi++)
+                    if (!history[pi]) { out[pi * 4] = pal[bgindex][0]; out[pi * 4 + 1] = pal[bgindex][1]; out[pi * 4 + 2] = pal[bgindex][2]; out[pi * 4 + 3] = 255; }
+            break;
+        } else if (tag == 0x21) {
+            const int ext = s.u8();
+            int n;
+            if (ext == 0xF9) {
+                n = s.u8();
+                if (n == 4) {
+                    eflags = s.u8();
+                    s.u16();
+                    if (transparent >= 0) pal[transparent][3] = 255;
+                    if (eflags & 1) { transparent = s.u8(); pal[transparent][3] = 0; }
+                    else { s.skip(1); transparent = -1; }
+                } else { s.skip(n); continue; }
+            }
+            while ((n = s.u8()) != 0) { s.skip(n); if (s.pos > s.n + 1024) { err = "Corrupt GIF"; return false; } }
+        } else if (tag == 0x3B) { err = "GIF without an image"; return false; }
+        else { err = "Corrupt GIF"; return false; }
+    }
+    rgb.resize(pcount * 3);
+    for (size_t i = 0; i < pcount; i++) { rgb[3 * i] = out[4 * i]; rgb[3 * i + 1] = out[4 * i + 1]; rgb[3 * i + 2] = out[4 * i + 2]; }
+    w = W;
+    h = H;
+    return true;
+}
+
+inline bool is_pnm(const unsigned char *b, size_t n) { return n >= 2 && b[0] == 'P' && (b[1] == '5' || b[1] == '6'); }
+
+inline bool decode_pnm(const unsigned char *bytes, size_t len, int &w, int &h, std::vector<unsigned char> &rgb, std::string &err) {
+    if (!is_pnm(bytes, len)) { err = "not PNM"; return false; }
+    Reader s(bytes, len);
+    s.skip(1);
+    const int comp = s.u8() == '6' ? 3 : 1;
+    int c = s.u8();
+    auto at_eof = [&]() { return s.pos >= s.n; };
+    auto is_space = [](int ch) { return ch == ' ' || ch == '\t' || ch == '\n' || ch == '\v' || ch == '\f' || ch == '\r'; };
+    auto skip_ws = [&]() {
+        for (;;) {
+            while (!at_eof() && is_space(c)) c = s.u8();
+            if (at_eof() || c != '#') break;
+            while (!at_eof() && c != '\n' && c != '\r') c = s.u8();
+        }
+    };
+    bool overflow = false;
+    auto integer = [&]() {
+        int value = 0;
+        while (!at_eof() && c >= '0' && c <= '9') {
+            value = value * 10 + (c - '0');
+            c = s.u8();
+            if (value > 214748364 || (value == 214748364 && c > '7')) { overflow = true; return 0; }
+        }
+        return value;
+    };
+    skip_ws();
+    const int W = integer();
+    if (W == 0 || overflow) { err = "PPM image header had zero or overflowing width"; return false; }
+    skip_ws();
+    const int H = integer();
+    if (H == 0 || overflow) { err = "PPM image header had zero or overflowing width"; return false; }
+    skip_ws();
+    const int maxv = integer();
+    if (overflow || maxv > 65535) { err = "PPM image supports only 8-bit and 16-bit images"; return false; }
+    const int bytes_per = maxv > 255 ? 2 : 1;
+    if (W > kMaxDimension || H > kMaxDimension) { err = "Very large image (corrupt?)"; return false; }
+    const uint64_t need = (uint64_t)W * (uint64_t)H * (uint64_t)comp * (uint64_t)bytes_per;
+    if (need > 0x7fffffffull) { err = "PNM too large"; return false; }
+    if (s.pos > s.n || need > s.n - s.pos) { err = "PNM file truncated"; return false; }
+    const unsigned char *px = bytes + s.pos;
+    const size_t n_px = (size_t)W * (size_t)H;
+    rgb.resize(n_px * 3);
+    for (size_t i = 0; i < n_px; i++)
+        for (int k = 0; k < 3; k++) {
+            const size_t sample = i * (size_t)comp + (size_t)(comp == 3 ? k : 0);
+            rgb[3 * i + (size_t)k] = bytes_per == 1 ? px[sample] : px[sample * 2 + 1];  // 16-bit: the second byte of the pair (see above)
+        }
+    w = W;
+    h = H;
     return true;
 }
 

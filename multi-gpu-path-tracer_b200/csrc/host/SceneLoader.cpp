@@ -396,9 +396,11 @@ HostTexture texture_from_bytes(const unsigned char *bytes, size_t n, const std::
         // BMP and TGA (texture files of an .mtl / .gltf): BmpTgaDecoder.h restates stb_image's choices for stbi_load(path, ..., 3), the call
         // the reference makes for files (src/HostScene.cpp:29); byte-identical texels, tests/golden/images/.  stb_image probes BMP before TGA
         // (TGA has no signature and is its last resort); GIF / PSD / PIC / PNM / HDR, which it probes in between, all fail the TGA test.
-        const bool bmp = ptimg::is_bmp(bytes, n);
-        if (bmp || ptimg::is_tga(bytes, n)) {
-            if (bmp ? ptimg::decode_bmp(bytes, n, w, h, px, err) : ptimg::decode_tga(bytes, n, w, h, px, err)) {
+        // probing order as in stb_image: BMP, GIF, (PSD, PIC: not read here,) PNM, (HDR,) and TGA last
+        const bool bmp = ptimg::is_bmp(bytes, n), gif = !bmp && ptimg::is_gif(bytes, n), pnm = !bmp && !gif && ptimg::is_pnm(bytes, n);
+        if (bmp || gif || pnm || ptimg::is_tga(bytes, n)) {
+            if (bmp ? ptimg::decode_bmp(bytes, n, w, h, px, err) : gif ? ptimg::decode_gif(bytes, n, w, h, px, err) : pnm ? ptimg::decode_pnm(bytes, n, w, h, px, err)
+                                                                                                                        : ptimg::decode_tga(bytes, n, w, h, px, err)) {
                 HostTexture t;
                 t.width = w;
                 t.height = h;
@@ -406,15 +408,15 @@ HostTexture texture_from_bytes(const unsigned char *bytes, size_t n, const std::
                 for (size_t j = 0; j < t.data.size(); j++) t.data[j] = make_float3((float)px[3 * j], (float)px[3 * j + 1], (float)px[3 * j + 2]);
                 return t;
             }
-            fprintf(stderr, "SceneLoader: %s texture %s: %s\n", bmp ? "BMP" : "TGA", what.c_str(), err.c_str());
+            fprintf(stderr, "SceneLoader: %s texture %s: %s\n", bmp ? "BMP" : gif ? "GIF" : pnm ? "PNM" : "TGA", what.c_str(), err.c_str());
         }
     }
     if (is_jpeg || !is_png) {
-        // The reference decodes textures with stb_image (src/HostScene.cpp:10-51), which also reads GIF / PSD / PIC / PNM / HDR; PNG, JPEG,
-        // BMP and TGA are restated here.  Any other image (or a variant stb_image refuses too, e.g. RLE BMP) does not abort the load: the material keeps its slot and gets a
+        // The reference decodes textures with stb_image (src/HostScene.cpp:10-51), which also reads PSD / PIC / HDR; PNG, JPEG,
+        // BMP, TGA, GIF (first frame) and binary PNM are restated here.  Any other image (or a variant stb_image refuses too, e.g. RLE BMP) does not abort the load: the material keeps its slot and gets a
         // texture without texels, which the device shades with the reference's own placeholder colour for a texture without data
         // (242, 45, 27: src/Texture.h:33-35).  README.md / INTEGRATION.md state the restriction.
-        const char *kind = is_jpeg ? "JPEG this decoder does not cover" : (n >= 2 && bytes[0] == 'B' && bytes[1] == 'M') ? "BMP variant that is not decoded" : "image format other than PNG / JPEG / BMP / TGA";
+        const char *kind = is_jpeg ? "JPEG this decoder does not cover" : (n >= 2 && bytes[0] == 'B' && bytes[1] == 'M') ? "BMP variant that is not decoded" : "image format other than PNG / JPEG / BMP / TGA / GIF / PNM";
         fprintf(stderr, "SceneLoader: texture %s is a %s; the placeholder colour (242, 45, 27) is used instead\n", what.c_str(), kind);
         HostTexture t;
         t.width = 1;

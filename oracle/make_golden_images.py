@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Golden texels for the repo's BMP / TGA readers, produced by the reference's own decoder (oracle/_ref/ref_stb = the vendored stb_image.h)
+"""Golden texels for the repo's BMP / TGA / GIF / PNM readers, produced by the reference's own decoder (oracle/_ref/ref_stb = the vendored stb_image.h)
 the way the reference calls it for a texture FILE: three requested channels (src/HostScene.cpp:29).
 
     python oracle/make_golden_images.py     (needs /root/reference for `make -C oracle _ref/ref_stb`; writes tests/golden/images/)
@@ -190,7 +190,25 @@ CASES = [
 ]
 
 
+def more_cases():
+    """GIF (first frame) and binary PNM files from the byte-level writers of tools/fuzz_gif_pnm.py, fixed seeds."""
+    import importlib.util, random
+    spec = importlib.util.spec_from_file_location("fuzz_gif_pnm", ROOT / "tools" / "fuzz_gif_pnm.py")
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    out = []
+    for k in range(12):
+        rnd, rng = random.Random(500 + k), np.random.default_rng(500 + k)
+        out.append((f"gif_handmade_{k}", "gif", (lambda d: (lambda: d))(fz.handmade_gif(rng, rnd))))
+    for k in range(8):
+        rnd, rng = random.Random(900 + k), np.random.default_rng(900 + k)
+        data = fz.pnm(rng, rnd)
+        out.append((f"pnm_{k}", "pgm" if data[:2] == b"P5" else "ppm", (lambda d: (lambda: d))(data)))
+    return out
+
+
 def main():
+    CASES.extend(more_cases())
     if not STB.exists():
         raise SystemExit("oracle/_ref/ref_stb missing: make -C oracle _ref/ref_stb (needs /root/reference)")
     OUT.mkdir(parents=True, exist_ok=True)

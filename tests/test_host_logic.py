@@ -408,16 +408,17 @@ def test_jpeg_textures_decode_to_the_texels_of_the_references_own_decoder(ptb, c
 
 
 def test_bmp_and_tga_textures_decode_to_the_texels_of_the_references_own_decoder(ptb, core_lib, tmp_path):
-    """tests/golden/images/*.bmp|tga with, beside each, what the reference's decoder returns for a texture FILE (stb_image with three
+    """tests/golden/images/*.bmp|tga|gif|pgm|ppm (GIF: first frame, sub-rectangles, background index, local tables, transparency, interlace;
+    PNM: P5 / P6, 8- and 16-bit, comments in the header) with, beside each, what the reference's decoder returns for a texture FILE (stb_image with three
     requested channels, src/HostScene.cpp:29; oracle/make_golden_images.py).  csrc/host/BmpTgaDecoder.h must give the SAME bytes for every
     header size, bit depth, palette, mask, orientation and RLE variant there — including stb_image's own quirk for a gap between a BMP
     header and its pixels — and must refuse (placeholder texture) what stb_image refuses.  When the reference-derived tool is present
     (build container) it is also run live."""
     import gzip
     idir = GOLD / "images"
-    files = sorted(p for p in idir.iterdir() if p.suffix in (".bmp", ".tga"))
+    files = sorted(p for p in idir.iterdir() if p.suffix in (".bmp", ".tga", ".gif", ".pgm", ".ppm"))
     refused = json.loads((idir / "refused.json").read_text())
-    assert len(files) >= 35 and len(refused) >= 1
+    assert len(files) >= 55 and len(refused) >= 1 and sum(p.suffix == ".gif" for p in files) >= 12
     stb = ROOT / "oracle" / "_ref" / "ref_stb"
     for path in files:
         sc = ptb.load_scene_file(_gltf_with_image(tmp_path, path.stem, path.read_bytes(), "image/" + path.suffix[1:]))
